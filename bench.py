@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point RK-steps per second of the daskol/nls hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload c2]
+
+A bench "step" is one pass of the hot path over the workload: one ``solve`` of `iters` RK4 steps.
+Default workload at every N is BASELINE.json configs[1] (C2: 2D 512 x 512 ring pumping, 5000 RK
+steps, order 5).  C2 does not shard ("replicas only"), so with --gpus N every rank
+advances its own replica (weak scaling, no data-path collective).  Other workloads (--workload c1,
+c3, c4, c5) are for DESIGN.md / profiles, not the driver's bench line.
+
+Output: ONE JSON line on rank 0 (see the keys in `main`).  `value` is device-timed with inputs resident
+in HBM; `e2e` goes through the f2py-signature entry point ``nls_b200.native.nls.solve_nls_2d`` with
+pinned HOST buffers (H2D + D2H inside the timed region).  `--impl reference` times the CPU oracle
+(``oracle/``: the C restatement of nls.f90 in the reference's own single precision -- the reference's
+Fortran cannot be compiled in this image) on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "grid-point RK-steps/sec"
+UNIT = "point-steps/s"
+BYTES_PER_POINT_STEP = 40.0      # read psi 16 + read P 8 + write psi 16
+
+ORIG = dict(R=0.0242057488654, gamma=0.0242057488654, g=0.00162178517398, tilde_g=0.0169440242057,
+            gamma_R=0.242057488654)
+
+WORKLOADS = {
+    # name: dim, n, batch, iters (per bench step), description
+    "c1": dict(dim=1, n=400, batch=1, iters=10000, desc="examples/solve1d.py: 1D radial n=400, ring pump, 10000 RK steps, order 5"),
+    "c2": dict(dim=2, n=512, batch=1, iters=5000, desc="examples/solve2d.py at 512x512: 2D ring pump, 5000 RK steps, order 5"),
+    "c3": dict(dim=1, n=1000, batch=65536, iters=1000, desc="1D ensemble 65536 members (256 powers x 256 reservoir rates), n=1000, order 5"),
+    "c4": dict(dim=2, n=8192, batch=1, iters=20, desc="2D 8192x8192 ring pump radius 200 var 50, order 5"),
+    "c5": dict(dim=2, n=1024, batch=256, iters=20, desc="2D ensemble 256 x 1024x1024, pump radius 2..40, order 5"),
+}
+
+
+def build_inputs(name, iters=None, batch=None):
+    """Synthetic inputs of the named shape (deterministic)."""
+    from nls_b200.model import Problem, dimensionless_coefficients
+    from nls_b200.pumping import GaussianRingPumping1D, GaussianRingPumping2D
+    w = dict(WORKLOADS[name])
+    if iters:
+        w["iters"] = iters
+    if batch:
+        w["batch"] = batch
+    n, B = w["n"], w["batch"]
+    coeffs = dimensionless_coefficients(dict(ORIG))
+    if name == "c1":
+        m = Problem().model(model="1d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
+                            pumping=GaussianRingPumping1D(power=20.0, radius=10.0, variation=3.14))
+        w.update(pumping=m.getPumping()[None], coeffs=coeffs[None], u0=m.getInitialSolution().astype(complex)[None])
+    elif name == "c2":
+        m = Problem().model(model="2d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
+                            pumping=GaussianRingPumping2D(power=20.0, radius=10.0, variation=3.14))
+        w.update(pumping=m.getPumping()[None], coeffs=coeffs[None], u0=m.getInitialSolution().astype(complex)[None])
+    elif name == "c3":
+        m = Problem().model(model="1d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
+                            pumping=GaussianRingPumping1D(power=1.0, radius=10.0, variation=3.14))
+        unit = m.getPumping()
+        side = int(round(np.sqrt(B)))
+        powers = np.linspace(1.0, 40.0, side)
+        gammas = np.geomspace(0.05, 1.0, max(B // side, 1))
+        P = (powers[:, None, None] * unit[None, None, :]) * np.ones((1, len(gammas), 1))
+        C = np.array([dimensionless_coefficients(dict(ORIG, gamma_R=g)) for g in gammas])
+        C = np.broadcast_to(C[None], (side, len(gammas), 23))
+        w.update(pumping=P.reshape(-1, n)[:B], coeffs=C.reshape(-1, 23)[:B].copy(), u0=np.full((B, n), 0.1 + 0j))
+    elif name == "c4":
+        m = Problem().model(model="2d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
+                            pumping=GaussianRingPumping2D(power=20.0, radius=200.0, variation=50.0))
+        w.update(pumping=m.getPumping()[None], coeffs=coeffs[None], u0=np.full((1, n, n), 0.1 + 0j))
+    elif name == "c5":
+        radii = np.linspace(2.0, 40.0, B)
+        P = np.empty((B, n, n))
+        for b, r in enumerate(radii):
+            m = Problem().model(model="2d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
+                                pumping=GaussianRingPumping2D(power=20.0, radius=float(r), variation=3.14))
+            P[b] = m.getPumping()
+        w.update(pumping=P, coeffs=np.broadcast_to(coeffs, (B, 23)).copy(), u0=np.full((B, n, n), 0.1 + 0j))
+    w.update(dx=0.1, dt=1e-3, order=5, name=name)
+    return w
+
+
+def points(w):
+    return w["batch"] * (w["n"] if w["dim"] == 1 else w["n"] * w["n"])
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(self.NAMES, r[3:7]):
+                if val == "Active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- reference arm: the CPU oracle ------------------------------------------------------------------
+def cpu_sample(w, kind="sp", budget_points=1.3e7):
+    """Times the oracle on a bounded sample of workload `w`: one member, `s` RK steps."""
+    from oracle import oracle as O
+    k = O.sp if kind == "sp" else O.dp
+    per_step = w["n"] if w["dim"] == 1 else w["n"] ** 2
+    s = int(max(2, min(w["iters"], budget_points // per_step)))
+    P, c, u0 = w["pumping"][0], w["coeffs"][0], w["u0"][0]
+    fn = k.solve_nls if w["dim"] == 1 else k.solve_nls_2d
+    t0 = time.perf_counter()
+    fn(w["dt"], w["dx"], w["order"], s, P, c, u0)
+    dt = time.perf_counter() - t0
+    sample = "1 member of %s, %d RK steps (%d point-steps), %s oracle, 1 thread" % (w["name"], s, per_step * s, kind)
+    return per_step * s / dt, dt, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = build_inputs(args.workload, args.iters, 1 if WORKLOADS[args.workload]["batch"] > 1 else None)
+    for _ in range(args.warmup):
+        cpu_sample(w, "sp", budget_points=2.0e6)
+    total_pts, total_t, sample = 0.0, 0.0, ""
+    for _ in range(args.steps):
+        rate, dt, sample = cpu_sample(w, "sp")
+        total_pts += rate * dt
+        total_t += dt
+    value = total_pts / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "name": w["name"],
+                   "note": "reference algorithm is serial; one bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---- engine arm -------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from nls_b200 import _lib
+    from nls_b200.engine import Ensemble1D, Grid2D
+    from nls_b200.native import nls
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl engine needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+
+    name = args.workload
+    spec = WORKLOADS[name]
+    # ensembles shard their members across ranks (strong scaling); single systems run as replicas (weak)
+    shard = spec["batch"] > 1
+    batch = None
+    if args.batch:
+        batch = args.batch
+    w = build_inputs(name, args.iters, batch)
+    if shard:
+        lo, hi = rank * w["batch"] // world, (rank + 1) * w["batch"] // world
+        for key in ("pumping", "coeffs", "u0"):
+            w[key] = w[key][lo:hi]
+        w["batch"] = hi - lo
+    iters = w["iters"]
+    dev = torch.device("cuda", local)
+
+    if w["dim"] == 1:
+        eng = Ensemble1D(w["n"], w["dx"], w["dt"], order=w["order"], batch=w["batch"], pumping=w["pumping"],
+                         coeffs=w["coeffs"], u0=w["u0"], device=dev)
+    else:
+        eng = Grid2D(w["n"], w["dx"], w["dt"], order=w["order"], batch=w["batch"], pumping=w["pumping"],
+                     coeffs=w["coeffs"], u0=w["u0"], device=dev)
+    psi0 = eng.psi.clone()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(timed):
+        eng.psi.copy_(psi0)
+        flush.zero_()
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.advance(iters)
+            b.record()
+            return a, b
+        eng.advance(iters)
+        return None
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    launches0 = _lib.kernel_launches()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        events = [one_step(True) for _ in range(args.steps)]
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = _lib.kernel_launches() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in events)
+    final = eng.psi.clone()
+
+    # end to end: host buffers through the reference-facing entry point (H2D + solve + D2H per step)
+    e2e = None
+    if name in ("c1", "c2", "c4"):
+        P_h = torch.from_numpy(np.ascontiguousarray(w["pumping"][0])).pin_memory().numpy()
+        u_h = torch.from_numpy(np.ascontiguousarray(w["u0"][0])).pin_memory().numpy()
+        c_h = w["coeffs"][0]
+        fn = nls.solve_nls if w["dim"] == 1 else nls.solve_nls_2d
+        for _ in range(max(1, min(args.warmup, 3))):
+            out = fn(w["dt"], w["dx"], w["order"], iters, P_h, c_h, u_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            out = fn(w["dt"], w["dx"], w["order"], iters, P_h, c_h, u_h)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_ok = bool(np.array_equal(out, final[0].cpu().numpy()))
+        e2e = (e2e_s, P_h.nbytes + u_h.nbytes + c_h.nbytes, out.nbytes, e2e_ok)
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e[0] if e2e else 0.0, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+
+    total_points = points(build_inputs(name, args.iters, batch)) if shard else points(w) * world
+    work = float(total_points) * iters * args.steps
+    value = work / (dev_ms_max * 1e-3)
+    peak, peak_src = measured_hbm_peak()
+    per_gpu_rate = value / world
+    achieved = BYTES_PER_POINT_STEP * per_gpu_rate / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "name": name, "rk_steps_per_bench_step": iters,
+                   "points_per_gpu": points(w), "partition": ("members sharded across ranks" if shard else "replicas only"),
+                   "l2": "256 MiB flush buffer written between timed steps; 512^2 working set is L2-resident by nature",
+                   "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
+        "gpu_launches": int(t[2]),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": "40 B per point-step x point-steps per launch (DESIGN.md)",
+                     "per": "GPU"},
+        "wall_s": t_wall,
+    }
+    if e2e:
+        line["e2e"] = {"value": float(points(w)) * world * iters * args.steps / e2e_s_max, "unit": UNIT,
+                       "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
+                       "api": "nls_b200.native.nls.solve_nls%s (C ABI nlsb_solve_nls%s, pinned host buffers)"
+                              % (("", "") if w["dim"] == 1 else ("_2d", "_2d")),
+                       "matches_device_run": e2e[3]}
+    line["clocks"] = clocks.summary()
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            wc = build_inputs(name, args.iters, 1 if spec["batch"] > 1 else None)
+            rate, dt_cpu, sample = cpu_sample(wc, "sp")
+            rate_dp, _, sample_dp = cpu_sample(wc, "dp", budget_points=6.0e6)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                                    "host_cores": os.cpu_count(), "dp_value": rate_dp, "dp_sample": sample_dp}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
+    ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

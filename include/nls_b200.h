@@ -1,0 +1,178 @@
+/*
+ * nls_b200.h -- C ABI of the B200 time-stepping engine for the daskol/nls hot path.
+ *
+ * The library (libnls_b200.so, built from nls_b200/csrc by nvcc for sm_100a) is the drop-in
+ * boundary: its entry points are what the reference's FFI for this path binds.  In the reference
+ * that FFI is the f2py extension `nls.native` generated from `module nls` of nls/nls.f90
+ * (setup.py:69-79, nls/makefile:45-50); each "host" entry point below takes the place of the
+ * Fortran routine cited next to it, with the same argument order and meaning.
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only, no exceptions, no torch / C++ types in any signature.
+ *   - Real kind: double.  The reference computes in real(sp) (nls.f90:10); this engine computes in
+ *     float64 / complex128 from the float64 inputs the Python layer builds (documented divergence,
+ *     DESIGN.md "Precision contract").  Complex arrays are interleaved (re, im) doubles.
+ *   - 2D arrays are n x n with the FIRST index contiguous, exactly as the Fortran dummy arguments
+ *     (numpy a[i, j] == Fortran a(i+1, j+1) == memory offset i + n*j).
+ *   - `coeffs` has 23 entries (nls.f90:770-786); only Fortran entries 3,4,5,6,12,13,14 are read.
+ *   - Return value: 0 on success; < 0 invalid argument (NLSB_E*); > 0 a cudaError_t.  A message for
+ *     the calling thread's last failure is returned by nlsb_last_error().  Unlike the reference,
+ *     which silently leaves the operator uninitialised for an unsupported order (nls.f90:293-294,
+ *     :396-402), these entry points fail with NLSB_EORDER.
+ *   - nlsb_* host entry points copy their inputs to the current CUDA device, run on an internal
+ *     stream, copy the result back and synchronise before returning.  Nothing is retained between
+ *     calls (the reference rebuilds its operator per call too, nls.f90:811, :917).
+ *   - nlsb_dev_* entry points take DEVICE pointers and a cudaStream_t (as void*), enqueue work and
+ *     return without synchronising.  They are what a device-resident caller (the Python layer with
+ *     torch tensors, the ensemble and slab drivers) uses.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef NLS_B200_H
+#define NLS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* every declaration below is an exported symbol of libnls_b200.so (the library itself is built with
+ * -fvisibility=hidden) */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define NLSB_OK        0
+#define NLSB_EINVAL   -1   /* null pointer / negative count */
+#define NLSB_EORDER   -2   /* order not in {3, 5, 7} */
+#define NLSB_ESIZE    -3   /* n too small for the stencil (n < order) or too large for the kernel */
+#define NLSB_ENOMEM   -4   /* host allocation failed */
+#define NLSB_EOPERATOR -5  /* operator table is not of the form the engine supports */
+
+typedef void *nlsb_stream_t;   /* cudaStream_t */
+
+const char *nlsb_last_error(void);
+/* 1 if a CUDA device is usable by this process, else 0 (never raises). */
+int nlsb_device_available(void);
+/* Number of CUDA kernels this library has launched since it was loaded (graph replays included). */
+unsigned long long nlsb_kernel_launches(void);
+
+/* ---- module nls, public routines (nls.f90:13-24) ------------------------------------------- */
+
+/* nls.f90:29-37  subroutine version(major, minor, patch) */
+void nlsb_version(int *major, int *minor, int *patch);
+
+/* nls.f90:61-91  make_banded_matrix(n, m, row, mat): mat is (m, n) column-major BLAS band storage */
+int nlsb_make_banded_matrix(int n, int m, const double *row, double *mat);
+/* nls.f90:93-107 */
+int nlsb_clear_first_row_of_derivative(int n, int m, double *L1);
+/* nls.f90:109-130 */
+int nlsb_divide_derivative_on_radius(int n, int m, double h, double *L1);
+/* nls.f90:132-295  make_laplacian[_o3|_o5|_o7](n, [m,] h, op): radial operator, op is (m, n) band */
+int nlsb_make_laplacian(int n, int m, double h, double *op);
+int nlsb_make_laplacian_o3(int n, double h, double *op);
+int nlsb_make_laplacian_o5(int n, double h, double *op);
+int nlsb_make_laplacian_o7(int n, double h, double *op);
+/* nls.f90:297-403  make_laplacian_2d[_o3|_o5|_o7](n, [m,] h, blocks, orders): blocks is (n, 2m-1).
+ * For m = 7 the intended 13-point cross stencil is built (the reference's own storage for that
+ * order is mis-dimensioned, nls.f90:360). */
+int nlsb_make_laplacian_2d(int n, int m, double h, double *blocks, int *orders);
+int nlsb_make_laplacian_2d_o3(int n, double h, double *blocks, int *orders);
+int nlsb_make_laplacian_2d_o5(int n, double h, double *blocks, int *orders);
+int nlsb_make_laplacian_2d_o7(int n, double h, double *blocks, int *orders);
+
+/* nls.f90:530-541  rgbmv(x, u, sign, op, klu, n):  u := u + sign * A x,  A banded (2klu+1, n) */
+int nlsb_rgbmv(const double *x, double *u, double sign, const double *op, int klu, int n);
+/* nls.f90:408-527  rbbmv[_o3|_o5|_o7](x, y, sign, blocks, ms, [m,] n):  y := y + sign * A x on n*n.
+ * The block operator must be line-independent along the second index (it always is when built by
+ * make_laplacian_2d); anything else fails with NLSB_EOPERATOR. */
+int nlsb_rbbmv(const double *x, double *y, double sign, const double *blocks, const int *ms, int m, int n);
+int nlsb_rbbmv_o3(const double *x, double *y, double sign, const double *blocks, const int *ms, int n);
+int nlsb_rbbmv_o5(const double *x, double *y, double sign, const double *blocks, const int *ms, int n);
+int nlsb_rbbmv_o7(const double *x, double *y, double sign, const double *blocks, const int *ms, int n);
+
+/* nls.f90:570-581 / :829-839  revervoir[_2d](pumping, coeffs, u_sqr, r, n) */
+int nlsb_revervoir(const double *pumping, const double *coeffs, const double *u_sqr, double *r, int n);
+int nlsb_revervoir_2d(const double *pumping, const double *coeffs, const double *u_sqr, double *r, int n);
+
+/* nls.f90:621-650  hamiltonian(pumping, coeffs, u, v, op, klu, n) */
+int nlsb_hamiltonian(const double *pumping, const double *coeffs, const double *u, double *v,
+                     const double *op, int klu, int n);
+/* nls.f90:841-870  hamiltonian_2d(pumping, coeffs, u, v, blocks, orders, order, n) */
+int nlsb_hamiltonian_2d(const double *pumping, const double *coeffs, const double *u, double *v,
+                        const double *blocks, const int *orders, int order, int n);
+
+/* nls.f90:705-734  runge_kutta(dt, t0, u0, op, n, order, iters, u, pumping, coeffs) */
+int nlsb_runge_kutta(double dt, double t0, const double *u0, const double *op, int n, int order, int iters,
+                     double *u, const double *pumping, const double *coeffs);
+/* nls.f90:873-901  runge_kutta_2d(dt, t0, u0, n, blocks, orders, order, iters, u, pumping, coeffs) */
+int nlsb_runge_kutta_2d(double dt, double t0, const double *u0, int n, const double *blocks, const int *orders,
+                        int order, int iters, double *u, const double *pumping, const double *coeffs);
+
+/* nls.f90:797-813, :815-827, :903-919  solve_nls[_1d|_2d](dt, dx, n, order, iters, pumping, coeffs, u0, u) */
+int nlsb_solve_nls(double dt, double dx, int n, int order, int iters, const double *pumping,
+                   const double *coeffs, const double *u0, double *u);
+int nlsb_solve_nls_1d(double dt, double dx, int n, int order, int iters, const double *pumping,
+                      const double *coeffs, const double *u0, double *u);
+int nlsb_solve_nls_2d(double dt, double dx, int n, int order, int iters, const double *pumping,
+                      const double *coeffs, const double *u0, double *u);
+
+/* nls.f90:921-948  chemical_potential_1d(dx, n, pumping, coeffs, u0, mu): mu is complex (2 doubles) */
+int nlsb_chemical_potential_1d(double dx, int n, const double *pumping, const double *coeffs,
+                               const double *u0, double *mu);
+/* nls.f90:950-971  chemical_potential_2d(dx, n, pumping, coeffs, u0, mu): mu is real */
+int nlsb_chemical_potential_2d(double dx, int n, const double *pumping, const double *coeffs,
+                               const double *u0, double *mu);
+
+/* ---- host-side operator tables in the engine's layout -------------------------------------- */
+
+/* Radial operator as a row-major tap table taps[i*m + t], t = s + k, multiplying x[i + s]
+ * (same numbers as make_laplacian, transposed out of band storage). */
+int nlsb_radial_taps(int n, int m, double h, double *taps);
+/* Band (m, n) -> tap table (n, m). */
+int nlsb_band_to_taps(int n, int m, const double *op, double *taps);
+/* Weights of the 2D cross stencil: wx[t] along the contiguous index (centre included), wy[t]
+ * across lines (wy[k] = 0), t = s + k. */
+int nlsb_cross_weights(int m, double h, double *wx, double *wy);
+/* Extract (wx, wy) from a block-band operator; NLSB_EOPERATOR if it is not line-independent. */
+int nlsb_blocks_to_weights(int n, int m, const double *blocks, const int *orders, double *wx, double *wy);
+
+/* ---- device-resident entry points (device pointers, asynchronous on `stream`) --------------- */
+
+/* Batched 1D radial systems sharing one tap table.  taps: [n][order]; pumping: [batch][n];
+ * coeffs: [batch][23]; psi: [batch][n] complex, advanced in place by `iters` RK4 steps.
+ * Each system lives in one CTA's registers / shared memory for the whole time loop. n <= 8192. */
+int nlsb_dev_rk4_1d(int batch, int n, int order, int iters, double dt, const double *taps,
+                    const double *pumping, const double *coeffs, double *psi, nlsb_stream_t stream);
+/* v = H(u) for a batch of 1D systems (one RHS evaluation, nls.f90:621-650). */
+int nlsb_dev_hamiltonian_1d(int batch, int n, int order, const double *taps, const double *pumping,
+                            const double *coeffs, const double *u, double *v, nlsb_stream_t stream);
+/* u := u + sign * A x, real vectors of length n. */
+int nlsb_dev_band_matvec_1d(int n, int order, const double *taps, const double *x, double *u, double sign,
+                            nlsb_stream_t stream);
+
+/* Batched 2D grids of rows x cols points (cols contiguous).  wx, wy: HOST arrays of `order` weights.
+ * pumping: [batch][rows][cols]; coeffs: DEVICE [batch][23]; psi: [batch][rows][cols] complex, in place.
+ * workspace: device scratch of nlsb_dev_rk4_2d_workspace() bytes. */
+size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols);
+int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
+                    const double *wy, const double *pumping, const double *coeffs, double *psi,
+                    void *workspace, size_t workspace_bytes, nlsb_stream_t stream);
+int nlsb_dev_hamiltonian_2d(int batch, int rows, int cols, int order, const double *wx, const double *wy,
+                            const double *pumping, const double *coeffs, const double *u, double *v,
+                            nlsb_stream_t stream);
+/* y := y + sign * A x, real fields of rows x cols. */
+int nlsb_dev_cross_matvec_2d(int rows, int cols, int order, const double *wx, const double *wy,
+                             const double *x, double *y, double sign, nlsb_stream_t stream);
+/* r = c12 P / (c13 + c14 u_sqr) on npts points (coeffs on the HOST). */
+int nlsb_dev_reservoir(size_t npts, const double *coeffs_host, const double *pumping, const double *u_sqr,
+                       double *r, nlsb_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLS_B200_H */

@@ -1,0 +1,642 @@
+// api.cu -- the C ABI of libnls_b200.so (see include/nls_b200.h for the contract and for the
+// reference routine each entry point stands in for).
+
+#include "kernels.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace nlsb {
+
+// ---- error channel ------------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+
+// Kernel launches issued by this library since load (launches replayed from a CUDA graph included).
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define NLSB_CUDA(expr)                                          \
+    do {                                                         \
+        cudaError_t e_ = (expr);                                 \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #expr);      \
+    } while (0)
+
+#define NLSB_TRY(expr)                 \
+    do {                               \
+        int rc_ = (expr);              \
+        if (rc_ != 0) {                \
+            if (rc_ > 0) cuda_fail((cudaError_t)rc_, #expr); \
+            return rc_;                \
+        }                              \
+    } while (0)
+
+int launch_weighted_dots(size_t npts, double radial_dx, const double2 *u0, const double2 *v, void *scratch,
+                         double *out4, cudaStream_t stream);
+size_t weighted_dots_scratch_bytes();
+
+namespace {
+
+bool valid_order(int m) { return m == 3 || m == 5 || m == 7; }
+
+int check_order_size(int n, int order)
+{
+    if (!valid_order(order)) return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+    if (n < order) return fail(NLSB_ESIZE, "n = %d is smaller than the stencil width %d", n, order);
+    return 0;
+}
+
+// Internal stream of the host-buffer entry points: one per (thread, device), created lazily.
+int internal_stream(cudaStream_t *out)
+{
+    static thread_local cudaStream_t streams[64] = {};
+    int dev = 0;
+    NLSB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(NLSB_EINVAL, "device ordinal %d out of range", dev);
+    if (!streams[dev]) NLSB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    *out = streams[dev];
+    return 0;
+}
+
+// Stream-ordered scratch allocations released when the scope ends (also on error paths).
+class Arena {
+public:
+    explicit Arena(cudaStream_t s) : stream_(s) {}
+    ~Arena()
+    {
+        for (void *p : ptrs_) cudaFreeAsync(p, stream_);
+    }
+    template <typename T>
+    int alloc(T **out, size_t count)
+    {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), stream_);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+        ptrs_.push_back(p);
+        *out = static_cast<T *>(p);
+        return 0;
+    }
+    template <typename T>
+    int upload(T **out, const T *host, size_t count)
+    {
+        NLSB_TRY(alloc(out, count));
+        NLSB_CUDA(cudaMemcpyAsync(*out, host, sizeof(T) * count, cudaMemcpyHostToDevice, stream_));
+        return 0;
+    }
+
+private:
+    cudaStream_t stream_;
+    std::vector<void *> ptrs_;
+};
+
+// ---- 2D time loop: 4 stage launches per RK step, replayed from a CUDA graph ----------------------
+void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const CrossWeights &w,
+                     const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream,
+                     int *rc)
+{
+    const size_t np = (size_t)batch * rows * cols;
+    double2 *ya = work, *yb = work + np, *acc = work + 2 * np;
+    Stage2DArgs a{batch, rows, cols, nullptr, psi, pumping, coeffs, acc, nullptr, 0.0, 1.0, dt / 6};
+    auto stage = [&](StageMode mode, const double2 *src, double2 *dst, double cy) {
+        a.ysrc = src;
+        a.ydst = dst;
+        a.cy = cy;
+        int r = launch_stage_2d(order, mode, w, a, stream);
+        if (r && !*rc) *rc = r;
+    };
+    stage(kStageFirst, psi, ya, dt / 2);
+    stage(kStageMid, ya, yb, dt / 2);
+    stage(kStageMid, yb, ya, dt);
+    stage(kStageLast, ya, psi, 0.0);
+}
+
+int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
+                   const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
+{
+    int rc = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NLSB_CUDA(cudaStreamIsCapturing(stream, &cap));
+    const int chunk = 16;
+    int done = 0;
+    if (cap == cudaStreamCaptureStatusNone && iters >= 2 * chunk) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        NLSB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        for (int s = 0; s < chunk; ++s) enqueue_step_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, stream, &rc);
+        cudaError_t e = cudaStreamEndCapture(stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+        count_launches(0ull - 4ull * chunk);   // the capture pass above only recorded, it did not run
+        for (; done + chunk <= iters; done += chunk) {
+            e = cudaGraphLaunch(exec, stream);
+            if (e != cudaSuccess) break;
+            count_launches(4ull * chunk);
+        }
+        // the executable graph is released once its in-flight launches complete
+        cudaGraphExecDestroy(exec);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+    }
+    for (; done < iters; ++done) enqueue_step_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, stream, &rc);
+    return rc;
+}
+
+int weights_from_host(int order, const double *wx, const double *wy, CrossWeights *w)
+{
+    if (!valid_order(order)) return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+    if (!wx || !wy) return fail(NLSB_EINVAL, "null stencil weights");
+    std::memset(w, 0, sizeof(*w));
+    for (int t = 0; t < order; ++t) {
+        w->wx[t] = wx[t];
+        w->wy[t] = wy[t];
+    }
+    return 0;
+}
+
+// ---- shared bodies of the host-buffer entry points ----------------------------------------------
+int host_rk4_1d(double dt, const double *taps_host, int n, int order, int iters, const double *pumping,
+                const double *coeffs, const double *u0, double *u)
+{
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    double *d_taps, *d_p, *d_c;
+    double2 *d_psi;
+    NLSB_TRY(mem.upload(&d_taps, taps_host, (size_t)n * order));
+    NLSB_TRY(mem.upload(&d_p, pumping, (size_t)n));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.upload(&d_psi, reinterpret_cast<const double2 *>(u0), (size_t)n));
+    NLSB_TRY(nlsb_dev_rk4_1d(1, n, order, iters, dt, d_taps, d_p, d_c, reinterpret_cast<double *>(d_psi), s));
+    NLSB_CUDA(cudaMemcpyAsync(u, d_psi, sizeof(double2) * n, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int host_rk4_2d(double dt, const CrossWeights &w, int n, int order, int iters, const double *pumping,
+                const double *coeffs, const double *u0, double *u)
+{
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    const size_t np = (size_t)n * n;
+    double *d_p, *d_c;
+    double2 *d_psi, *d_work;
+    NLSB_TRY(mem.upload(&d_p, pumping, np));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.upload(&d_psi, reinterpret_cast<const double2 *>(u0), np));
+    NLSB_TRY(mem.alloc(&d_work, 3 * np));
+    NLSB_TRY(enqueue_rk4_2d(1, n, n, order, iters, dt, w, d_p, d_c, d_psi, d_work, s));
+    NLSB_CUDA(cudaMemcpyAsync(u, d_psi, sizeof(double2) * np, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int host_hamiltonian_1d(const double *taps_host, int n, int order, const double *pumping, const double *coeffs,
+                        const double *u, double *v, double *mu_out /* optional: chemical potential */, double dx)
+{
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    double *d_taps, *d_p, *d_c;
+    double2 *d_u, *d_v;
+    NLSB_TRY(mem.upload(&d_taps, taps_host, (size_t)n * order));
+    NLSB_TRY(mem.upload(&d_p, pumping, (size_t)n));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.upload(&d_u, reinterpret_cast<const double2 *>(u), (size_t)n));
+    NLSB_TRY(mem.alloc(&d_v, (size_t)n));
+    NLSB_TRY(launch_hamiltonian_1d(1, n, order, d_taps, d_p, d_c, d_u, d_v, s));
+    if (v) NLSB_CUDA(cudaMemcpyAsync(v, d_v, sizeof(double2) * n, cudaMemcpyDeviceToHost, s));
+    if (mu_out) {
+        char *scratch;
+        double *d_out;
+        NLSB_TRY(mem.alloc(&scratch, weighted_dots_scratch_bytes()));
+        NLSB_TRY(mem.alloc(&d_out, (size_t)4));
+        NLSB_TRY(launch_weighted_dots((size_t)n, dx, d_u, d_v, scratch, d_out, s));
+        NLSB_CUDA(cudaMemcpyAsync(mu_out, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int host_hamiltonian_2d(const CrossWeights &w, int n, int order, const double *pumping, const double *coeffs,
+                        const double *u, double *v, double *mu_out)
+{
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    const size_t np = (size_t)n * n;
+    double *d_p, *d_c;
+    double2 *d_u, *d_v;
+    NLSB_TRY(mem.upload(&d_p, pumping, np));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.upload(&d_u, reinterpret_cast<const double2 *>(u), np));
+    NLSB_TRY(mem.alloc(&d_v, np));
+    Stage2DArgs a{1, n, n, d_u, d_u, d_p, d_c, nullptr, d_v, 0.0, 0.0, 0.0};
+    NLSB_TRY(launch_stage_2d(order, kStageRhs, w, a, s));
+    if (v) NLSB_CUDA(cudaMemcpyAsync(v, d_v, sizeof(double2) * np, cudaMemcpyDeviceToHost, s));
+    if (mu_out) {
+        char *scratch;
+        double *d_out;
+        NLSB_TRY(mem.alloc(&scratch, weighted_dots_scratch_bytes()));
+        NLSB_TRY(mem.alloc(&d_out, (size_t)4));
+        NLSB_TRY(launch_weighted_dots(np, 0.0, d_u, d_v, scratch, d_out, s));
+        NLSB_CUDA(cudaMemcpyAsync(mu_out, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// mu = i*E'/M from the four sums {Re M, Im M, Re E', Im E'} (nls.f90:946-947, :968-970)
+void chemical_potential_from_dots(const double d[4], double mu[2])
+{
+    const double er = -d[3], ei = d[2];   // (0,1) * E'
+    const double den = d[0] * d[0] + d[1] * d[1];
+    mu[0] = (er * d[0] + ei * d[1]) / den;
+    mu[1] = (ei * d[0] - er * d[1]) / den;
+}
+
+}  // namespace
+}  // namespace nlsb
+
+using namespace nlsb;
+
+extern "C" {
+
+const char *nlsb_last_error(void) { return g_error; }
+
+unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nlsb_device_available(void)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count > 0 ? 1 : 0;
+}
+
+void nlsb_version(int *major, int *minor, int *patch)
+{
+    if (major) *major = 0;
+    if (minor) *minor = 2;
+    if (patch) *patch = 0;
+}
+
+// ---- operator builders (host) ---------------------------------------------------------------------
+int nlsb_make_banded_matrix(int n, int m, const double *row, double *mat)
+{
+    if (!row || !mat || n < 1) return fail(NLSB_EINVAL, "make_banded_matrix: bad arguments");
+    return banded_from_row(n, m, row, mat);
+}
+
+int nlsb_clear_first_row_of_derivative(int n, int m, double *L1)
+{
+    if (!L1 || n < 1 || m < 1 || (m & 1) == 0 || n < m) return fail(NLSB_EINVAL, "clear_first_row_of_derivative: bad arguments");
+    const int k = (m - 1) / 2;
+    for (int j = 0; j <= k; ++j) L1[(size_t)(k - j) + (size_t)m * j] = 0.0;   // entries A(0, j)
+    return 0;
+}
+
+int nlsb_divide_derivative_on_radius(int n, int m, double h, double *L1)
+{
+    if (!L1 || n < 1 || m < 1 || (m & 1) == 0) return fail(NLSB_EINVAL, "divide_derivative_on_radius: bad arguments");
+    const int k = (m - 1) / 2;
+    for (int j = 0; j < n; ++j)
+        for (int b = 0; b < m; ++b) {
+            const int rho = j + b - k;   // matrix row of band entry (b, j)
+            if (rho > 0) L1[(size_t)b + (size_t)m * j] = L1[(size_t)b + (size_t)m * j] / ((double)rho * h);
+        }
+    return 0;
+}
+
+int nlsb_radial_taps(int n, int m, double h, double *taps)
+{
+    if (!taps || n < 1) return fail(NLSB_EINVAL, "radial_taps: bad arguments");
+    return radial_taps(n, m, h, taps);
+}
+
+int nlsb_band_to_taps(int n, int m, const double *op, double *taps)
+{
+    if (!op || !taps || n < 1) return fail(NLSB_EINVAL, "band_to_taps: bad arguments");
+    return band_to_taps(n, m, op, taps);
+}
+
+int nlsb_make_laplacian(int n, int m, double h, double *op)
+{
+    if (!op || n < 1) return fail(NLSB_EINVAL, "make_laplacian: bad arguments");
+    NLSB_TRY(check_order_size(n, m));
+    std::vector<double> taps((size_t)n * m);
+    NLSB_TRY(radial_taps(n, m, h, taps.data()));
+    return taps_to_band(n, m, taps.data(), op);
+}
+int nlsb_make_laplacian_o3(int n, double h, double *op) { return nlsb_make_laplacian(n, 3, h, op); }
+int nlsb_make_laplacian_o5(int n, double h, double *op) { return nlsb_make_laplacian(n, 5, h, op); }
+int nlsb_make_laplacian_o7(int n, double h, double *op) { return nlsb_make_laplacian(n, 7, h, op); }
+
+int nlsb_make_laplacian_2d(int n, int m, double h, double *blocks, int *orders)
+{
+    if (!blocks || !orders || n < 1) return fail(NLSB_EINVAL, "make_laplacian_2d: bad arguments");
+    return cross_blocks(n, m, h, blocks, orders);
+}
+int nlsb_make_laplacian_2d_o3(int n, double h, double *b, int *o) { return nlsb_make_laplacian_2d(n, 3, h, b, o); }
+int nlsb_make_laplacian_2d_o5(int n, double h, double *b, int *o) { return nlsb_make_laplacian_2d(n, 5, h, b, o); }
+int nlsb_make_laplacian_2d_o7(int n, double h, double *b, int *o) { return nlsb_make_laplacian_2d(n, 7, h, b, o); }
+
+int nlsb_cross_weights(int m, double h, double *wx, double *wy)
+{
+    if (!wx || !wy) return fail(NLSB_EINVAL, "cross_weights: bad arguments");
+    return cross_weights(m, h, wx, wy);
+}
+
+int nlsb_blocks_to_weights(int n, int m, const double *blocks, const int *orders, double *wx, double *wy)
+{
+    if (!blocks || !orders || !wx || !wy) return fail(NLSB_EINVAL, "blocks_to_weights: bad arguments");
+    return blocks_to_weights(n, m, blocks, orders, wx, wy);
+}
+
+// ---- matvecs / reservoir (host buffers) -----------------------------------------------------------
+int nlsb_rgbmv(const double *x, double *u, double sign, const double *op, int klu, int n)
+{
+    if (!x || !u || !op || n < 1 || klu < 0 || klu > 3) return fail(NLSB_EINVAL, "rgbmv: bad arguments");
+    const int m = 2 * klu + 1;
+    if (n < m) return fail(NLSB_ESIZE, "n = %d is smaller than the band width %d", n, m);
+    std::vector<double> taps((size_t)n * m);
+    NLSB_TRY(band_to_taps(n, m, op, taps.data()));
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    double *d_taps, *d_x, *d_u;
+    NLSB_TRY(mem.upload(&d_taps, taps.data(), taps.size()));
+    NLSB_TRY(mem.upload(&d_x, x, (size_t)n));
+    NLSB_TRY(mem.upload(&d_u, u, (size_t)n));
+    NLSB_TRY(launch_band_matvec_1d(n, m, d_taps, d_x, d_u, sign, s));
+    NLSB_CUDA(cudaMemcpyAsync(u, d_u, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int nlsb_rbbmv(const double *x, double *y, double sign, const double *blocks, const int *ms, int m, int n)
+{
+    if (!x || !y || !blocks || !ms || n < 1) return fail(NLSB_EINVAL, "rbbmv: bad arguments");
+    CrossWeights w{};
+    NLSB_TRY(blocks_to_weights(n, m, blocks, ms, w.wx, w.wy));
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    const size_t np = (size_t)n * n;
+    double *d_x, *d_y;
+    NLSB_TRY(mem.upload(&d_x, x, np));
+    NLSB_TRY(mem.upload(&d_y, y, np));
+    NLSB_TRY(launch_cross_matvec_2d(n, n, m, w, d_x, d_y, sign, s));
+    NLSB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+int nlsb_rbbmv_o3(const double *x, double *y, double sg, const double *b, const int *ms, int n) { return nlsb_rbbmv(x, y, sg, b, ms, 3, n); }
+int nlsb_rbbmv_o5(const double *x, double *y, double sg, const double *b, const int *ms, int n) { return nlsb_rbbmv(x, y, sg, b, ms, 5, n); }
+int nlsb_rbbmv_o7(const double *x, double *y, double sg, const double *b, const int *ms, int n) { return nlsb_rbbmv(x, y, sg, b, ms, 7, n); }
+
+static int host_reservoir(const double *pumping, const double *coeffs, const double *u_sqr, double *r, size_t np)
+{
+    if (!pumping || !coeffs || !u_sqr || !r) return fail(NLSB_EINVAL, "revervoir: null argument");
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    double *d_p, *d_q, *d_r;
+    NLSB_TRY(mem.upload(&d_p, pumping, np));
+    NLSB_TRY(mem.upload(&d_q, u_sqr, np));
+    NLSB_TRY(mem.alloc(&d_r, np));
+    NLSB_TRY(launch_reservoir(np, rhs_coeffs_from(coeffs), d_p, d_q, d_r, s));
+    NLSB_CUDA(cudaMemcpyAsync(r, d_r, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int nlsb_revervoir(const double *pumping, const double *coeffs, const double *u_sqr, double *r, int n)
+{
+    if (n < 1) return fail(NLSB_EINVAL, "revervoir: n must be positive");
+    return host_reservoir(pumping, coeffs, u_sqr, r, (size_t)n);
+}
+
+int nlsb_revervoir_2d(const double *pumping, const double *coeffs, const double *u_sqr, double *r, int n)
+{
+    if (n < 1) return fail(NLSB_EINVAL, "revervoir_2d: n must be positive");
+    return host_reservoir(pumping, coeffs, u_sqr, r, (size_t)n * n);
+}
+
+// ---- right-hand side, time stepping, solve (host buffers) -----------------------------------------
+int nlsb_hamiltonian(const double *pumping, const double *coeffs, const double *u, double *v, const double *op,
+                     int klu, int n)
+{
+    if (!pumping || !coeffs || !u || !v || !op) return fail(NLSB_EINVAL, "hamiltonian: null argument");
+    const int m = 2 * klu + 1;
+    NLSB_TRY(check_order_size(n, m));
+    std::vector<double> taps((size_t)n * m);
+    NLSB_TRY(band_to_taps(n, m, op, taps.data()));
+    return host_hamiltonian_1d(taps.data(), n, m, pumping, coeffs, u, v, nullptr, 0.0);
+}
+
+int nlsb_hamiltonian_2d(const double *pumping, const double *coeffs, const double *u, double *v, const double *blocks,
+                        const int *orders, int order, int n)
+{
+    if (!pumping || !coeffs || !u || !v || !blocks || !orders) return fail(NLSB_EINVAL, "hamiltonian_2d: null argument");
+    NLSB_TRY(check_order_size(n, order));
+    CrossWeights w{};
+    NLSB_TRY(blocks_to_weights(n, order, blocks, orders, w.wx, w.wy));
+    return host_hamiltonian_2d(w, n, order, pumping, coeffs, u, v, nullptr);
+}
+
+int nlsb_runge_kutta(double dt, double t0, const double *u0, const double *op, int n, int order, int iters, double *u,
+                     const double *pumping, const double *coeffs)
+{
+    (void)t0;   // the pumping is time independent; the reference advances t but never reads it
+    if (!u0 || !op || !u || !pumping || !coeffs || iters < 0) return fail(NLSB_EINVAL, "runge_kutta: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    std::vector<double> taps((size_t)n * order);
+    NLSB_TRY(band_to_taps(n, order, op, taps.data()));
+    return host_rk4_1d(dt, taps.data(), n, order, iters, pumping, coeffs, u0, u);
+}
+
+int nlsb_runge_kutta_2d(double dt, double t0, const double *u0, int n, const double *blocks, const int *orders,
+                        int order, int iters, double *u, const double *pumping, const double *coeffs)
+{
+    (void)t0;
+    if (!u0 || !blocks || !orders || !u || !pumping || !coeffs || iters < 0)
+        return fail(NLSB_EINVAL, "runge_kutta_2d: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    CrossWeights w{};
+    NLSB_TRY(blocks_to_weights(n, order, blocks, orders, w.wx, w.wy));
+    return host_rk4_2d(dt, w, n, order, iters, pumping, coeffs, u0, u);
+}
+
+int nlsb_solve_nls(double dt, double dx, int n, int order, int iters, const double *pumping, const double *coeffs,
+                   const double *u0, double *u)
+{
+    if (!pumping || !coeffs || !u0 || !u || iters < 0) return fail(NLSB_EINVAL, "solve_nls: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    std::vector<double> taps((size_t)n * order);
+    NLSB_TRY(radial_taps(n, order, dx, taps.data()));
+    return host_rk4_1d(dt, taps.data(), n, order, iters, pumping, coeffs, u0, u);
+}
+
+int nlsb_solve_nls_1d(double dt, double dx, int n, int order, int iters, const double *pumping, const double *coeffs,
+                      const double *u0, double *u)
+{
+    return nlsb_solve_nls(dt, dx, n, order, iters, pumping, coeffs, u0, u);
+}
+
+int nlsb_solve_nls_2d(double dt, double dx, int n, int order, int iters, const double *pumping, const double *coeffs,
+                      const double *u0, double *u)
+{
+    if (!pumping || !coeffs || !u0 || !u || iters < 0) return fail(NLSB_EINVAL, "solve_nls_2d: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    CrossWeights w{};
+    NLSB_TRY(cross_weights(order, dx, w.wx, w.wy));
+    return host_rk4_2d(dt, w, n, order, iters, pumping, coeffs, u0, u);
+}
+
+int nlsb_chemical_potential_1d(double dx, int n, const double *pumping, const double *coeffs, const double *u0,
+                               double *mu)
+{
+    if (!pumping || !coeffs || !u0 || !mu) return fail(NLSB_EINVAL, "chemical_potential_1d: null argument");
+    const int order = 5;   // hard-wired in the reference (nls.f90:931)
+    NLSB_TRY(check_order_size(n, order));
+    if (!(dx > 0.0)) return fail(NLSB_EINVAL, "chemical_potential_1d: dx must be positive");
+    std::vector<double> taps((size_t)n * order);
+    NLSB_TRY(radial_taps(n, order, dx, taps.data()));
+    double dots[4];
+    NLSB_TRY(host_hamiltonian_1d(taps.data(), n, order, pumping, coeffs, u0, nullptr, dots, dx));
+    chemical_potential_from_dots(dots, mu);
+    return 0;
+}
+
+int nlsb_chemical_potential_2d(double dx, int n, const double *pumping, const double *coeffs, const double *u0,
+                               double *mu)
+{
+    if (!pumping || !coeffs || !u0 || !mu) return fail(NLSB_EINVAL, "chemical_potential_2d: null argument");
+    const int order = 5;   // nls.f90:958
+    NLSB_TRY(check_order_size(n, order));
+    CrossWeights w{};
+    NLSB_TRY(cross_weights(order, dx, w.wx, w.wy));
+    double dots[4], both[2];
+    NLSB_TRY(host_hamiltonian_2d(w, n, order, pumping, coeffs, u0, nullptr, dots));
+    chemical_potential_from_dots(dots, both);
+    *mu = both[0];   // the reference's result is real(sp): the imaginary part is dropped (nls.f90:955)
+    return 0;
+}
+
+// ---- device-resident entry points -----------------------------------------------------------------
+int nlsb_dev_rk4_1d(int batch, int n, int order, int iters, double dt, const double *taps, const double *pumping,
+                    const double *coeffs, double *psi, nlsb_stream_t stream)
+{
+    if (!taps || !pumping || !coeffs || !psi || batch < 1 || iters < 0) return fail(NLSB_EINVAL, "dev_rk4_1d: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double2 *p = reinterpret_cast<double2 *>(psi);
+    if (n <= kMaxResident1D) {
+        NLSB_TRY(launch_rk4_1d(batch, n, order, iters, dt, taps, pumping, coeffs, p, s));
+        return 0;
+    }
+    Arena mem(s);
+    double2 *work;
+    NLSB_TRY(mem.alloc(&work, 3 * (size_t)batch * n));
+    NLSB_TRY(launch_rk4_1d_staged(batch, n, order, iters, dt, taps, pumping, coeffs, p, work, s));
+    return 0;
+}
+
+int nlsb_dev_hamiltonian_1d(int batch, int n, int order, const double *taps, const double *pumping,
+                            const double *coeffs, const double *u, double *v, nlsb_stream_t stream)
+{
+    if (!taps || !pumping || !coeffs || !u || !v || batch < 1) return fail(NLSB_EINVAL, "dev_hamiltonian_1d: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    NLSB_TRY(launch_hamiltonian_1d(batch, n, order, taps, pumping, coeffs, reinterpret_cast<const double2 *>(u),
+                                   reinterpret_cast<double2 *>(v), static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_band_matvec_1d(int n, int order, const double *taps, const double *x, double *u, double sign,
+                            nlsb_stream_t stream)
+{
+    if (!taps || !x || !u || n < 1) return fail(NLSB_EINVAL, "dev_band_matvec_1d: bad arguments");
+    NLSB_TRY(launch_band_matvec_1d(n, order, taps, x, u, sign, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols)
+{
+    if (batch < 1 || rows < 1 || cols < 1) return 0;
+    return sizeof(double2) * 3 * (size_t)batch * rows * cols;
+}
+
+int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
+                    const double *wy, const double *pumping, const double *coeffs, double *psi, void *workspace,
+                    size_t workspace_bytes, nlsb_stream_t stream)
+{
+    if (!pumping || !coeffs || !psi || !workspace || batch < 1 || iters < 0) return fail(NLSB_EINVAL, "dev_rk4_2d: bad arguments");
+    NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
+    if (workspace_bytes < nlsb_dev_rk4_2d_workspace(batch, rows, cols))
+        return fail(NLSB_EINVAL, "dev_rk4_2d: workspace of %zu bytes is too small", workspace_bytes);
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    NLSB_TRY(enqueue_rk4_2d(batch, rows, cols, order, iters, dt, w, pumping, coeffs, reinterpret_cast<double2 *>(psi),
+                            static_cast<double2 *>(workspace), static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_hamiltonian_2d(int batch, int rows, int cols, int order, const double *wx, const double *wy,
+                            const double *pumping, const double *coeffs, const double *u, double *v,
+                            nlsb_stream_t stream)
+{
+    if (!pumping || !coeffs || !u || !v || batch < 1) return fail(NLSB_EINVAL, "dev_hamiltonian_2d: bad arguments");
+    NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    const double2 *uu = reinterpret_cast<const double2 *>(u);
+    Stage2DArgs a{batch, rows, cols, uu, uu, pumping, coeffs, nullptr, reinterpret_cast<double2 *>(v), 0.0, 0.0, 0.0};
+    NLSB_TRY(launch_stage_2d(order, kStageRhs, w, a, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_cross_matvec_2d(int rows, int cols, int order, const double *wx, const double *wy, const double *x,
+                             double *y, double sign, nlsb_stream_t stream)
+{
+    if (!x || !y || rows < 1 || cols < 1) return fail(NLSB_EINVAL, "dev_cross_matvec_2d: bad arguments");
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    NLSB_TRY(launch_cross_matvec_2d(rows, cols, order, w, x, y, sign, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_reservoir(size_t npts, const double *coeffs_host, const double *pumping, const double *u_sqr, double *r,
+                       nlsb_stream_t stream)
+{
+    if (!coeffs_host || !pumping || !u_sqr || !r) return fail(NLSB_EINVAL, "dev_reservoir: null argument");
+    NLSB_TRY(launch_reservoir(npts, rhs_coeffs_from(coeffs_host), pumping, u_sqr, r, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// device_math.cuh -- pointwise right-hand side shared by every kernel.
+#pragma once
+
+#include "internal.h"
+
+#include <cuda_runtime.h>
+
+namespace nlsb {
+
+// Pointwise part of v = H(u) plus the Laplacian terms (nls.f90:637-647 / :857-867):
+//     n   = c12*P / (c13 + c14*|u|^2)                       reservoir, closed form (nls.f90:580)
+//     a   = c3*n - c4 ,  b = c5*|u|^2 + c6*n
+//     v   = (a*u_re + b*u_im - L u_im) + i (a*u_im - b*u_re + L u_re)
+// `cp` is the product c12*P (the reference's own left-to-right association, formed once per solve).
+// The divide is IEEE round-to-nearest, as in the reference.
+__device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, double2 u, double lap_re, double lap_im)
+{
+    const double usq = fma(u.x, u.x, u.y * u.y);
+    const double res = cp / fma(c.c14, usq, c.c13);
+    const double a = fma(c.c3, res, -c.c4);
+    const double b = fma(c.c5, usq, c.c6 * res);
+    double2 v;
+    v.x = fma(a, u.x, fma(b, u.y, -lap_im));
+    v.y = fma(a, u.y, fma(-b, u.x, lap_re));
+    return v;
+}
+
+__device__ __forceinline__ RhsCoeffs load_rhs_coeffs(const double *__restrict__ coeffs23)
+{
+    RhsCoeffs c;
+    c.c3 = coeffs23[2];
+    c.c4 = coeffs23[3];
+    c.c5 = coeffs23[4];
+    c.c6 = coeffs23[5];
+    c.c12 = coeffs23[11];
+    c.c13 = coeffs23[12];
+    c.c14 = coeffs23[13];
+    return c;
+}
+
+}  // namespace nlsb

@@ -1,0 +1,46 @@
+// kernels.h -- launchers implemented in the .cu files; called by api.cu.  All pointers are device
+// pointers unless stated otherwise.  Each launcher returns a cudaError_t-compatible int (0 = ok) or
+// a negative NLSB_E* code.
+#pragma once
+
+#include "internal.h"
+
+#include <cuda_runtime.h>
+
+namespace nlsb {
+
+enum StageMode { kStageRhs = 0, kStageFirst = 1, kStageMid = 2, kStageLast = 3 };
+
+// kernels_1d.cu
+constexpr int kMaxResident1D = 2048;   // largest n the CTA-resident 1D kernel handles (8 nodes x 256 threads)
+int launch_rk4_1d(int batch, int n, int order, int iters, double dt, const double *taps, const double *pumping,
+                  const double *coeffs, double2 *psi, cudaStream_t stream);
+// n > kMaxResident1D: per-stage launches through global memory; work holds 3*batch*n complex values
+int launch_rk4_1d_staged(int batch, int n, int order, int iters, double dt, const double *taps,
+                         const double *pumping, const double *coeffs, double2 *psi, double2 *work,
+                         cudaStream_t stream);
+int launch_hamiltonian_1d(int batch, int n, int order, const double *taps, const double *pumping,
+                          const double *coeffs, const double2 *u, double2 *v, cudaStream_t stream);
+int launch_band_matvec_1d(int n, int order, const double *taps, const double *x, double *u, double sign,
+                          cudaStream_t stream);
+
+// kernels_2d.cu
+struct Stage2DArgs {
+    int batch, rows, cols;
+    const double2 *ysrc;    // stage input (stencil source)
+    const double2 *ubase;   // u at the beginning of the step
+    const double *pumping;
+    const double *coeffs;   // [batch][23]
+    double2 *acc;           // k1 + 2 k2 + 2 k3 (read and written in place)
+    double2 *ydst;          // next stage input, or v for kStageRhs, or u for kStageLast
+    double cy;              // dt/2 or dt
+    double cacc;            // weight of k in acc (1 or 2)
+    double dt6;             // dt/6
+};
+int launch_stage_2d(int order, StageMode mode, const CrossWeights &w, const Stage2DArgs &a, cudaStream_t stream);
+int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
+                           double sign, cudaStream_t stream);
+int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,
+                     cudaStream_t stream);
+
+}  // namespace nlsb

@@ -1,0 +1,186 @@
+// kernels_2d.cu -- per-stage 2D kernels for sm_100a (one launch per RK stage).
+//
+// stage_2d_kernel evaluates k = H(y) on a rows x cols grid (cols contiguous) with the separable
+// cross stencil of make_laplacian_2d (nls.f90:297-385; truncated = zero outside the square) and
+// folds the RK4 stage algebra of runge_kutta_2d (nls.f90:892-899) into the same pass:
+//     first  : acc = k,         y' = u + cy*k
+//     middle : acc += 2k,       y' = u + cy*k
+//     last   : u  = u + (acc + k)*dt/6
+//     rhs    : v  = k                                  (hamiltonian_2d, nls.f90:841-870)
+// Every thread owns one complex128 node: a warp reads 512 contiguous bytes per row, the x-taps hit
+// the same L1 lines, the y-taps are L1/L2 hits from the neighbouring rows of the CTA tile.
+// This is the simple 4-pass formulation (expected DRAM traffic 56+88+88+72 B per node-step, see
+// DESIGN.md); the fused-step kernel in fused_2d.cu is the fast path for whole time loops.
+
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace nlsb {
+
+namespace {
+
+template <int K>
+struct WeightsK {
+    double wx[2 * K + 1];
+    double wy[2 * K + 1];
+};
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(256)
+stage_2d_kernel(int rows, int cols, WeightsK<K> w, const double2 *__restrict__ ysrc,
+                const double2 *__restrict__ ubase, const double *__restrict__ pumping,
+                const double *__restrict__ coeffs, double2 *__restrict__ acc, double2 *__restrict__ ydst,
+                double cy, double dt6)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const size_t member = blockIdx.z;
+    const size_t plane = (size_t)rows * cols;
+    const size_t g = member * plane + (size_t)y * cols + x;
+    const double2 *src = ysrc + member * plane;
+    const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
+
+    const double2 centre = src[(size_t)y * cols + x];
+    double lr = w.wx[K] * centre.x, li = w.wx[K] * centre.y;
+#pragma unroll
+    for (int s = 1; s <= K; ++s) {
+        if (x - s >= 0) {
+            const double2 v = src[(size_t)y * cols + (x - s)];
+            lr = fma(w.wx[K - s], v.x, lr);
+            li = fma(w.wx[K - s], v.y, li);
+        }
+        if (x + s < cols) {
+            const double2 v = src[(size_t)y * cols + (x + s)];
+            lr = fma(w.wx[K + s], v.x, lr);
+            li = fma(w.wx[K + s], v.y, li);
+        }
+        if (y - s >= 0) {
+            const double2 v = src[(size_t)(y - s) * cols + x];
+            lr = fma(w.wy[K - s], v.x, lr);
+            li = fma(w.wy[K - s], v.y, li);
+        }
+        if (y + s < rows) {
+            const double2 v = src[(size_t)(y + s) * cols + x];
+            lr = fma(w.wy[K + s], v.x, lr);
+            li = fma(w.wy[K + s], v.y, li);
+        }
+    }
+    const double2 k = rhs_point(c, c.c12 * pumping[g], centre, lr, li);
+
+    if (MODE == kStageRhs) {
+        ydst[g] = k;
+    } else if (MODE == kStageFirst) {
+        const double2 u = centre;   // ysrc == ubase in the first stage
+        acc[g] = k;
+        ydst[g] = make_double2(fma(k.x, cy, u.x), fma(k.y, cy, u.y));
+    } else if (MODE == kStageMid) {
+        const double2 u = ubase[g], a = acc[g];
+        acc[g] = make_double2(fma(2.0, k.x, a.x), fma(2.0, k.y, a.y));
+        ydst[g] = make_double2(fma(k.x, cy, u.x), fma(k.y, cy, u.y));
+    } else {
+        const double2 u = ubase[g], a = acc[g];
+        ydst[g] = make_double2(fma(a.x + k.x, dt6, u.x), fma(a.y + k.y, dt6, u.y));
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+cross_matvec_2d_kernel(int rows, int cols, WeightsK<K> w, const double *__restrict__ xin, double *__restrict__ yio,
+                       double sign)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    double s = w.wx[K] * xin[(size_t)y * cols + x];
+#pragma unroll
+    for (int d = 1; d <= K; ++d) {
+        if (x - d >= 0) s = fma(w.wx[K - d], xin[(size_t)y * cols + (x - d)], s);
+        if (x + d < cols) s = fma(w.wx[K + d], xin[(size_t)y * cols + (x + d)], s);
+        if (y - d >= 0) s = fma(w.wy[K - d], xin[(size_t)(y - d) * cols + x], s);
+        if (y + d < rows) s = fma(w.wy[K + d], xin[(size_t)(y + d) * cols + x], s);
+    }
+    const size_t g = (size_t)y * cols + x;
+    yio[g] = fma(sign, s, yio[g]);
+}
+
+__global__ void reservoir_kernel(size_t npts, RhsCoeffs c, const double *__restrict__ pumping,
+                                 const double *__restrict__ u_sqr, double *__restrict__ r)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts; t += stride)
+        r[t] = c.c12 * pumping[t] / (c.c13 + c.c14 * u_sqr[t]);   // nls.f90:580 / :838
+}
+
+template <int K>
+WeightsK<K> pack(const CrossWeights &w)
+{
+    WeightsK<K> p;
+    for (int t = 0; t < 2 * K + 1; ++t) {
+        p.wx[t] = w.wx[t];
+        p.wy[t] = w.wy[t];
+    }
+    return p;
+}
+
+template <int K>
+int launch_stage_k(StageMode mode, const CrossWeights &w, const Stage2DArgs &a, cudaStream_t stream)
+{
+    const dim3 block(64, 4);
+    const dim3 grid((a.cols + block.x - 1) / block.x, (a.rows + block.y - 1) / block.y, a.batch);
+    const WeightsK<K> p = pack<K>(w);
+#define NLSB_LAUNCH_STAGE(MODE)                                                                         \
+    stage_2d_kernel<K, MODE><<<grid, block, 0, stream>>>(a.rows, a.cols, p, a.ysrc, a.ubase, a.pumping, \
+                                                         a.coeffs, a.acc, a.ydst, a.cy, a.dt6)
+    switch (mode) {
+    case kStageRhs: NLSB_LAUNCH_STAGE(kStageRhs); break;
+    case kStageFirst: NLSB_LAUNCH_STAGE(kStageFirst); break;
+    case kStageMid: NLSB_LAUNCH_STAGE(kStageMid); break;
+    case kStageLast: NLSB_LAUNCH_STAGE(kStageLast); break;
+    }
+#undef NLSB_LAUNCH_STAGE
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_stage_2d(int order, StageMode mode, const CrossWeights &w, const Stage2DArgs &a, cudaStream_t stream)
+{
+    if (a.batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid z-limit 65535", a.batch);
+    switch (order) {
+    case 3: return launch_stage_k<1>(mode, w, a, stream);
+    case 5: return launch_stage_k<2>(mode, w, a, stream);
+    case 7: return launch_stage_k<3>(mode, w, a, stream);
+    }
+    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
+
+int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
+                           double sign, cudaStream_t stream)
+{
+    const dim3 block(64, 4);
+    const dim3 grid((cols + block.x - 1) / block.x, (rows + block.y - 1) / block.y);
+    switch (order) {
+    case 3: cross_matvec_2d_kernel<1><<<grid, block, 0, stream>>>(rows, cols, pack<1>(w), x, y, sign); break;
+    case 5: cross_matvec_2d_kernel<2><<<grid, block, 0, stream>>>(rows, cols, pack<2>(w), x, y, sign); break;
+    case 7: cross_matvec_2d_kernel<3><<<grid, block, 0, stream>>>(rows, cols, pack<3>(w), x, y, sign); break;
+    default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+    }
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,
+                     cudaStream_t stream)
+{
+    if (npts == 0) return 0;
+    const int block = 256;
+    size_t blocks = (npts + block - 1) / block;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    reservoir_kernel<<<(unsigned)blocks, block, 0, stream>>>(npts, c, pumping, u_sqr, r);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace nlsb

@@ -1,0 +1,171 @@
+"""Device-resident front-end of the engine: torch tensors in HBM, kernels through the C ABI.
+
+PyTorch is plumbing here -- it owns the complex128/float64 device buffers, the CUDA streams and (for
+multi-GPU) ``torch.distributed``; every arithmetic kernel is in ``libnls_b200.so``.
+
+What this adds on top of ``nls_b200.native`` (which copies host arrays in and out on every call like the
+reference's f2py module does):
+
+* state that stays on the GPU between calls (``Ensemble1D`` / ``Grid2D`` objects: psi, pumping,
+  coefficient table and operator tables are uploaded once; ``advance(iters)`` can be called
+  repeatedly -- the continuation pattern of ``tools/check.py:34-36`` and ``nls/animation.py:64-67``);
+* the batched-ensemble mode: many independent parameter points (per-member ``coeffs[23]`` and
+  pumping profile) advanced by one launch.
+
+Reference semantics per member are those of ``solve_nls`` / ``solve_nls_2d`` (nls.f90:797-813,
+:903-919).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["Ensemble1D", "Grid2D", "radial_taps", "cross_weights", "require_cuda"]
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("nls_b200.engine needs a CUDA device: the engine has no CPU fallback")
+
+
+def _dptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def radial_taps(n, order, dx):
+    """Row-major tap table of the radial operator (host, float64, bit-identical to make_laplacian)."""
+    taps = np.zeros((n, order), dtype=np.float64)
+    _lib.call("nlsb_radial_taps", int(n), int(order), float(dx), taps.ctypes.data_as(C.c_void_p))
+    return taps
+
+
+def cross_weights(order, dx):
+    """(wx, wy) weights of the 2D cross stencil (host, float64, bit-identical to make_laplacian_2d)."""
+    wx, wy = np.zeros(order), np.zeros(order)
+    _lib.call("nlsb_cross_weights", int(order), float(dx), wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p))
+    return wx, wy
+
+
+def _coeff_table(coeffs, batch):
+    c = np.asarray(coeffs, dtype=np.float64)
+    if c.ndim == 1:
+        c = np.broadcast_to(c, (batch, 23))
+    if c.shape != (batch, 23):
+        raise ValueError("coeffs must have shape (23,) or (batch, 23); got %r" % (c.shape,))
+    return np.ascontiguousarray(c)
+
+
+def _to_device(a, dtype, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+
+
+class Ensemble1D(object):
+    """``batch`` independent radial systems of ``n`` nodes sharing dx, dt and the stencil order.
+
+    pumping: (batch, n) or (n,); coeffs: (batch, 23) or (23,); u0: (batch, n), (n,) or scalar.
+    """
+
+    def __init__(self, n, dx, dt, order=5, batch=1, pumping=None, coeffs=None, u0=0.1, device=None):
+        require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n, self.dx, self.dt, self.order, self.batch = int(n), float(dx), float(dt), int(order), int(batch)
+        with torch.cuda.device(self.device):
+            self.taps = _to_device(radial_taps(self.n, self.order, self.dx), torch.float64, self.device)
+            self.coeffs = _to_device(_coeff_table(coeffs, self.batch), torch.float64, self.device)
+            self.pumping = self._field(pumping, torch.float64)
+            self.psi = self._field(u0, torch.complex128)
+        self.steps_done = 0
+
+    def _field(self, value, dtype):
+        if isinstance(value, (int, float, complex)):
+            return torch.full((self.batch, self.n), value, dtype=dtype, device=self.device)
+        t = _to_device(value, dtype, self.device)
+        if t.ndim == 1:
+            t = t.unsqueeze(0).expand(self.batch, self.n).contiguous()
+        if tuple(t.shape) != (self.batch, self.n):
+            raise ValueError("expected shape (%d, %d), got %r" % (self.batch, self.n, tuple(t.shape)))
+        return t
+
+    def advance(self, iters):
+        """``iters`` RK4 steps of every member, in place, asynchronously on the current stream."""
+        with torch.cuda.device(self.device):
+            _lib.call("nlsb_dev_rk4_1d", self.batch, self.n, self.order, int(iters), self.dt, _dptr(self.taps),
+                      _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi), _stream())
+        self.steps_done += int(iters)
+        return self
+
+    def hamiltonian(self, u=None):
+        u = self.psi if u is None else _to_device(u, torch.complex128, self.device)
+        v = torch.empty_like(u)
+        with torch.cuda.device(self.device):
+            _lib.call("nlsb_dev_hamiltonian_1d", self.batch, self.n, self.order, _dptr(self.taps), _dptr(self.pumping),
+                      _dptr(self.coeffs), _dptr(u), _dptr(v), _stream())
+        return v
+
+    def solution(self):
+        return self.psi.cpu().numpy()
+
+
+class Grid2D(object):
+    """``batch`` independent n x n (or rows x cols) Cartesian grids sharing dx, dt and the order.
+
+    pumping: (batch, rows, cols) or (rows, cols); coeffs: (batch, 23) or (23,); u0 likewise or scalar.
+    """
+
+    def __init__(self, n, dx, dt, order=5, batch=1, pumping=None, coeffs=None, u0=0.1, device=None, cols=None):
+        require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rows, self.cols = int(n), int(n if cols is None else cols)
+        self.dx, self.dt, self.order, self.batch = float(dx), float(dt), int(order), int(batch)
+        self.wx, self.wy = cross_weights(self.order, self.dx)
+        with torch.cuda.device(self.device):
+            self.coeffs = _to_device(_coeff_table(coeffs, self.batch), torch.float64, self.device)
+            self.pumping = self._field(pumping, torch.float64)
+            self.psi = self._field(u0, torch.complex128)
+            nbytes = _lib.load().nlsb_dev_rk4_2d_workspace(self.batch, self.rows, self.cols)
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.steps_done = 0
+
+    def _field(self, value, dtype):
+        shape = (self.batch, self.rows, self.cols)
+        if isinstance(value, (int, float, complex)):
+            return torch.full(shape, value, dtype=dtype, device=self.device)
+        t = _to_device(value, dtype, self.device)
+        if t.ndim == 2:
+            t = t.unsqueeze(0).expand(*shape).contiguous()
+        if tuple(t.shape) != shape:
+            raise ValueError("expected shape %r, got %r" % (shape, tuple(t.shape)))
+        return t
+
+    def _w(self, a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def advance(self, iters):
+        with torch.cuda.device(self.device):
+            _lib.call("nlsb_dev_rk4_2d", self.batch, self.rows, self.cols, self.order, int(iters), self.dt,
+                      self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi),
+                      _dptr(self.workspace), C.c_size_t(self.workspace.numel()), _stream())
+        self.steps_done += int(iters)
+        return self
+
+    def hamiltonian(self, u=None):
+        u = self.psi if u is None else _to_device(u, torch.complex128, self.device)
+        v = torch.empty_like(u)
+        with torch.cuda.device(self.device):
+            _lib.call("nlsb_dev_hamiltonian_2d", self.batch, self.rows, self.cols, self.order, self._w(self.wx),
+                      self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), _dptr(u), _dptr(v), _stream())
+        return v
+
+    def solution(self):
+        return self.psi.cpu().numpy()

@@ -1,0 +1,107 @@
+"""The C-ABI library loads, exports every symbol include/nls_b200.h declares, its host-side operator
+builders are bit-identical to the dp oracle, and compute entry points fail loudly without a GPU."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nls_b200 import _lib
+from nls_b200.native import nls, error
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nls_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nlsb_\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_prototyped():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 40
+    for name in names:
+        assert hasattr(lib, name), "libnls_b200.so does not export %s" % name
+        assert name in _lib.PROTOTYPES, "no ctypes prototype for %s" % name
+    assert sorted(_lib.PROTOTYPES) == names
+
+
+def test_library_is_built_for_sm_100a():
+    log = os.path.join(ROOT, "nls_b200", "build.log")
+    if os.path.exists(log):
+        assert "arch=compute_100a,code=sm_100a" in open(log).read()
+
+
+def test_version_and_error_channel():
+    assert nls.version() == (0, 2, 0)
+    with pytest.raises(error) as info:
+        nls.make_laplacian(32, 4, 0.1)                 # the reference would return garbage (nls.f90:293-294)
+    assert info.value.status == -2 and "order" in str(info.value)
+    with pytest.raises(error) as info:
+        nls.make_laplacian_2d(4, 7, 0.1)
+    assert info.value.status == -3
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+@pytest.mark.parametrize("n,h", [(7, 0.01), (40, 0.1), (400, 0.1), (1000, 0.05)])
+def test_operator_builders_bit_exact_vs_oracle(order, n, h):
+    assert np.array_equal(nls.make_laplacian(n, order, h), O.dp.make_laplacian(n, order, h))
+    blocks, orders = nls.make_laplacian_2d(n, order, h)
+    oblocks, oorders = O.dp.make_laplacian_2d(n, order, h)
+    assert np.array_equal(blocks, oblocks) and np.array_equal(orders, oorders)
+
+
+def test_band_helpers_match_oracle():
+    row = [1.0, 2.0, 3.0, 4.0, 5.0]
+    assert np.array_equal(nls.make_banded_matrix(7, row), O.dp.make_banded_matrix(7, row))
+    rng = np.random.default_rng(3)
+    L1 = np.asfortranarray(rng.standard_normal((5, 9)))
+    a = nls.clear_first_row_of_derivative(L1)
+    b = L1.copy(order="F")
+    O._load().nlso_clear_first_row_of_derivative_dp(C.c_int(9), C.c_int(5), b.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, b)
+    a = nls.divide_derivative_on_radius(0.3, L1)
+    b = L1.copy(order="F")
+    O._load().nlso_divide_derivative_on_radius_dp(C.c_int(9), C.c_int(5), C.c_double(0.3), b.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, b)
+
+
+def test_taps_and_weights_tables():
+    lib = _lib.load()
+    n, m, h = 50, 5, 0.1
+    taps = np.zeros((n, m))
+    assert lib.nlsb_radial_taps(n, m, h, taps.ctypes.data_as(C.c_void_p)) == 0
+    op = O.dp.make_laplacian(n, m, h)
+    dense = np.zeros((n, n))
+    for j in range(n):
+        for b in range(m):
+            i = j + b - 2
+            if 0 <= i < n:
+                dense[i, j] = op[b, j]
+    for i in range(n):
+        for t in range(m):
+            j = i + t - 2
+            assert taps[i, t] == (dense[i, j] if 0 <= j < n else 0.0)
+    wx, wy = np.zeros(m), np.zeros(m)
+    blocks, orders = O.dp.make_laplacian_2d(n, m, h)
+    assert lib.nlsb_blocks_to_weights(n, m, blocks.ctypes.data_as(C.c_void_p), orders.ctypes.data_as(C.c_void_p),
+                                      wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p)) == 0
+    dx2 = 12 * (h * h)
+    assert np.array_equal(wx, np.array([-1, 16, -60, 16, -1]) / dx2)
+    assert np.array_equal(wy, np.array([-1, 16, 0, 16, -1]) / dx2)
+    blocks[3, 1] *= 2.0      # a line-dependent off-diagonal block is not a cross stencil
+    assert lib.nlsb_blocks_to_weights(n, m, blocks.ctypes.data_as(C.c_void_p), orders.ctypes.data_as(C.c_void_p),
+                                      wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p)) == -5
+
+
+def test_compute_fails_loudly_without_a_device():
+    if _lib.device_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(error) as info:
+        nls.solve_nls(1e-3, 0.1, 5, 1, np.ones(16), np.ones(23), np.ones(16) * 0.1)
+    assert info.value.status > 0          # a cudaError_t: no CPU fallback exists

@@ -1,0 +1,223 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the dp oracle on identical inputs.
+
+Bar (BASELINE.json north_star): relative L2 error <= 1e-10 in complex128 after a fixed horizon;
+single right-hand-side evaluations and matvecs are held to 1e-13.  The engine uses fused
+multiply-adds and its own summation order, the oracle follows nls.f90's order without contraction,
+so bitwise equality is not expected -- the tolerances are written next to each assertion.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ORIG = dict(R=0.0242057488654, gamma=0.0242057488654, g=0.00162178517398, tilde_g=0.0169440242057,
+            gamma_R=0.242057488654)
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+
+
+def model_1d(n, iters=100, order=5, power=20.0):
+    from nls_b200.model import Problem
+    from nls_b200.pumping import GaussianRingPumping1D
+    return Problem().model(model="1d", dx=0.1, dt=1e-3, u0=0.1, order=order, num_nodes=n, num_iters=iters,
+                           pumping=GaussianRingPumping1D(power=power, radius=10.0, variation=3.14),
+                           original_params=dict(ORIG))
+
+
+def model_2d(n, iters=100, order=5, radius=10.0, dx=0.1):
+    from nls_b200.model import Problem
+    from nls_b200.pumping import GaussianRingPumping2D
+    return Problem().model(model="2d", dx=dx, dt=1e-3, u0=0.1, order=order, num_nodes=n, num_iters=iters,
+                           pumping=GaussianRingPumping2D(power=20.0, radius=radius, variation=3.14),
+                           original_params=dict(ORIG))
+
+
+def rough_field(shape, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * 0.3
+
+
+@pytest.fixture(scope="module")
+def nls():
+    from nls_b200.native import nls as native
+    from nls_b200 import _lib
+    assert _lib.device_available(), "the GPU tests need a CUDA device"
+    return native
+
+
+# ---- matvecs, reservoir, right-hand side ------------------------------------------------------------
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+@pytest.mark.parametrize("n", [7, 33, 400, 1000])
+def test_rgbmv(nls, order, n):
+    rng = np.random.default_rng(order * 100 + n)
+    op = O.dp.make_laplacian(n, order, 0.1)
+    x, u = rng.standard_normal(n), rng.standard_normal(n)
+    want = O.dp.rgbmv(x, u, -1.0, op)
+    nls.rgbmv(x, u, -1.0, op)
+    assert np.abs(u - want).max() <= 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+def test_rbbmv(nls, order):
+    n = 37
+    rng = np.random.default_rng(order)
+    blocks, orders = O.dp.make_laplacian_2d(n, order, 0.2)
+    x, y = rng.standard_normal(n * n), rng.standard_normal(n * n)
+    want = O.dp.rbbmv(x, y, 1.0, blocks, orders, n)
+    nls.rbbmv(x, y, 1.0, blocks, orders, n)
+    assert np.abs(y - want).max() <= 1e-13 * np.abs(want).max()
+
+
+def test_revervoir(nls):
+    rng = np.random.default_rng(5)
+    c = model_1d(16).getCoefficients()
+    p, q = rng.random(1000) * 20, rng.random(1000) * 4
+    assert np.array_equal(nls.revervoir(p, c, q), O.dp.revervoir(p, c, q))       # one mul, one fma-free divide
+    p2, q2 = rng.random((31, 31)) * 20, rng.random((31, 31)) * 4
+    got = nls.revervoir_2d(p2, c, q2)
+    assert np.abs(got - O.dp.revervoir(p2, c, q2)).max() <= 1e-15 * 20
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+@pytest.mark.parametrize("n", [7, 50, 401])
+def test_hamiltonian_1d(nls, order, n):
+    m = model_1d(n, order=order)
+    u = rough_field(n, n + order)
+    op = O.dp.make_laplacian(n, order, m.dx)
+    want = O.dp.hamiltonian(m.getPumping(), m.getCoefficients(), u, op)
+    got = nls.hamiltonian(m.getPumping(), m.getCoefficients(), u, op)
+    assert rel_l2(got, want) <= 1e-13
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+@pytest.mark.parametrize("n", [7, 64, 101])
+def test_hamiltonian_2d(nls, order, n):
+    m = model_2d(n, order=order)
+    u = rough_field((n, n), n + order)
+    blocks, orders = O.dp.make_laplacian_2d(n, order, m.dx)
+    want = O.dp.hamiltonian_2d(m.getPumping(), m.getCoefficients(), u, blocks, orders)
+    got = nls.hamiltonian_2d(m.getPumping(), m.getCoefficients(), u, blocks, orders)
+    assert got.shape == (n, n) and rel_l2(got, want) <= 1e-13
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+# ---- time stepping ---------------------------------------------------------------------------------
+
+def test_solve_1d_reference_example_full_horizon(nls):
+    """BASELINE config 1 = examples/solve1d.py: n=400, 10 000 steps, order 5, ring pump."""
+    m = model_1d(400, 10000)
+    args = (m.dt, m.dx, 5, 10000, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    want = O.dp.solve_nls(*args)
+    got = nls.solve_nls(*args)
+    assert got.dtype == np.complex128 and got.shape == (400,)
+    assert rel_l2(got, want) <= 1e-10
+    # the shipped single-precision algorithm agrees to f32 drift: both restate the same algorithm
+    assert rel_l2(got, O.sp.solve_nls(*args)) <= 5e-4
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+@pytest.mark.parametrize("n", [7, 100, 1000, 1100, 2048])
+def test_solve_1d_sizes_and_orders(nls, order, n):
+    m = model_1d(n, 200, order=order)
+    args = (m.dt, m.dx, order, 200, m.getPumping(), m.getCoefficients(), rough_field(n, n) * 0.1 + 0.1)
+    assert rel_l2(nls.solve_nls(*args), O.dp.solve_nls(*args)) <= 1e-10
+    assert rel_l2(nls.solve_nls_1d(*args), O.dp.solve_nls(*args)) <= 1e-10
+
+
+def test_solve_1d_larger_than_one_cta(nls):
+    n = 3000      # beyond the CTA-resident kernel: staged fallback through global memory
+    m = model_1d(n, 50)
+    args = (m.dt, m.dx, 5, 50, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    assert rel_l2(nls.solve_nls(*args), O.dp.solve_nls(*args)) <= 1e-10
+
+
+def test_runge_kutta_with_caller_supplied_band(nls):
+    n = 300
+    m = model_1d(n, 100, order=7)
+    op = O.dp.make_laplacian(n, 7, m.dx)
+    u0 = rough_field(n, 9) * 0.2
+    want = O.dp.runge_kutta(m.dt, 0.0, u0, op, 100, m.getPumping(), m.getCoefficients())
+    got = nls.runge_kutta(m.dt, 0.0, u0, op, 100, m.getPumping(), m.getCoefficients())
+    assert rel_l2(got, want) <= 1e-10
+
+
+@pytest.mark.parametrize("order,n,iters", [(3, 40, 300), (5, 7, 50), (5, 96, 500), (5, 129, 200), (7, 64, 300)])
+def test_solve_2d(nls, order, n, iters):
+    m = model_2d(n, iters, order=order, radius=min(10.0, n * 0.1 / 4))
+    args = (m.dt, m.dx, order, iters, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    want = O.dp.solve_nls_2d(*args)
+    got = nls.solve_nls_2d(*args)
+    assert got.shape == (n, n) and got.dtype == np.complex128
+    assert rel_l2(got, want) <= 1e-10
+
+
+def test_solve_2d_nonsymmetric_input_keeps_index_convention(nls):
+    # a[i, j] <-> Fortran a(i+1, j+1): an asymmetric pump/initial field must come back un-transposed
+    n = 48
+    m = model_2d(n, 100)
+    rng = np.random.default_rng(2)
+    P = m.getPumping() * (1.0 + 0.5 * rng.random((n, n)))
+    u0 = rough_field((n, n), 3) * 0.2
+    args = (m.dt, m.dx, 5, 100, P, m.getCoefficients(), u0)
+    assert rel_l2(nls.solve_nls_2d(*args), O.dp.solve_nls_2d(*args)) <= 1e-10
+    blocks, orders = O.dp.make_laplacian_2d(n, 5, m.dx)
+    got = nls.runge_kutta_2d(m.dt, 0.0, u0, blocks, orders, 100, P, m.getCoefficients())
+    assert rel_l2(got, O.dp.solve_nls_2d(*args)) <= 1e-10
+
+
+def test_solve_2d_c2_size_short_horizon(nls):
+    """BASELINE config 2 grid (512 x 512, ring pump) against the oracle for 20 steps."""
+    m = model_2d(512, 20)
+    args = (m.dt, m.dx, 5, 20, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    assert rel_l2(nls.solve_nls_2d(*args), O.dp.solve_nls_2d(*args)) <= 1e-10
+
+
+def test_chemical_potentials(nls):
+    m = model_1d(400, 500)
+    P, c = m.getPumping(), m.getCoefficients()
+    u = O.dp.solve_nls(m.dt, m.dx, 5, 500, P, c, m.getInitialSolution())
+    want = O.dp.chemical_potential_1d(m.dx, P, c, u)
+    got = nls.chemical_potential_1d(m.dx, P, c, u)
+    assert isinstance(got, complex) and abs(got - want) <= 1e-12 * abs(want)
+    m2 = model_2d(64, 100)
+    P2 = m2.getPumping()
+    u2 = O.dp.solve_nls_2d(m2.dt, m2.dx, 5, 100, P2, c, m2.getInitialSolution())
+    want2 = O.dp.chemical_potential_2d(m2.dx, P2, c, u2)
+    got2 = nls.chemical_potential_2d(m2.dx, P2, c, u2)
+    assert isinstance(got2, float) and abs(got2 - want2) <= 1e-12 * abs(want2)
+
+
+def test_object_api_end_to_end(nls, capsys):
+    m = model_1d(400, 1000)
+    sol = m.solve()
+    sol.report()
+    assert "1000 iteration on 400 grid nodes" in capsys.readouterr().out
+    want = O.dp.solve_nls(m.dt, m.dx, 5, 1000, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    assert rel_l2(sol.getSolution(), want) <= 1e-10
+    mu = m.getChemicalPotential(sol)
+    assert abs(mu - O.dp.chemical_potential_1d(m.dx, m.getPumping(), m.getCoefficients(), want)) <= 1e-9 * abs(mu)
+    m2 = model_2d(64, 100)
+    sol2 = m2.solve()
+    want2 = O.dp.solve_nls_2d(m2.dt, m2.dx, 5, 100, m2.getPumping(), m2.getCoefficients(), m2.getInitialSolution())
+    assert rel_l2(sol2.getSolution(), want2) <= 1e-10
+
+
+def test_errors(nls):
+    from nls_b200.native import error
+    with pytest.raises(error):
+        nls.solve_nls(1e-3, 0.1, 4, 1, np.ones(16), np.ones(23), np.ones(16))     # bad order
+    with pytest.raises(error):
+        nls.solve_nls_2d(1e-3, 0.1, 7, 1, np.ones((5, 5)), np.ones(23), np.ones((5, 5)))   # n < order
+    with pytest.raises(ValueError):
+        nls.solve_nls(1e-3, 0.1, 5, 1, np.ones(16), np.ones(22), np.ones(16))     # coeffs must be 23
+    with pytest.raises(ValueError):
+        nls.solve_nls(1e-3, 0.1, 5, 1, np.ones(16), np.ones(23), np.ones(17))
+    # zero iterations returns the input
+    u0 = rough_field(32, 1)
+    assert np.array_equal(nls.solve_nls(1e-3, 0.1, 5, 0, np.ones(32), np.ones(23), u0), u0)
