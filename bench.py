@@ -206,6 +206,8 @@ def run_engine(args):
     from nls_b200 import _lib
     from nls_b200.engine import Ensemble1D, Grid2D
     from nls_b200.native import nls
+    from nls_b200.engine import set_2d_path
+    set_2d_path(args.path)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -311,6 +313,7 @@ def run_engine(args):
         "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "name": name, "rk_steps_per_bench_step": iters,
                    "points_per_gpu": points(w), "partition": ("members sharded across ranks" if shard else "replicas only"),
+                   "kernels_2d": args.path,
                    "l2": "256 MiB flush buffer written between timed steps; 512^2 working set is L2-resident by nature",
                    "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
         "gpu_launches": int(t[2]),
@@ -351,6 +354,7 @@ def main():
     ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--path", choices=["auto", "fused", "staged"], default="auto", help="2D kernel family")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

@@ -127,8 +127,77 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
     stage(kStageLast, ya, psi, 0.0);
 }
 
+// Fused path: one launch per RK step, psi ping-pongs between `psi` and the first plane of `work`.
+void enqueue_fused_steps_2d(int batch, int rows, int cols, int order, double dt, const CrossWeights &w,
+                            const double *pumping, const double *coeffs, double2 *psi, double2 *work, int first_step,
+                            int nsteps, cudaStream_t stream, int *rc)
+{
+    Fused2DStep s{batch, rows, cols, 0, rows, 0, rows, nullptr, nullptr, pumping, coeffs, dt};
+    for (int i = 0; i < nsteps; ++i) {
+        const bool even = ((first_step + i) & 1) == 0;
+        s.in = even ? psi : work;
+        s.out = even ? work : psi;
+        int r = launch_rk4_step_fused_2d(order, s, w, stream);
+        if (r && !*rc) *rc = r;
+    }
+}
+
+int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
+                         const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
+{
+    int rc = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NLSB_CUDA(cudaStreamIsCapturing(stream, &cap));
+    const int chunk = 32;   // even: a replayed chunk starts and ends in `psi`
+    int done = 0;
+    if (cap == cudaStreamCaptureStatusNone && iters >= 2 * chunk) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t rec;
+        NLSB_TRY(internal_stream(&rec));
+        NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
+        enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, &rc);
+        cudaError_t e = cudaStreamEndCapture(rec, &graph);
+        count_launches(0ull - (unsigned long long)chunk);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+        for (; done + chunk <= iters; done += chunk) {
+            e = cudaGraphLaunch(exec, stream);
+            if (e != cudaSuccess) break;
+            count_launches((unsigned long long)chunk);
+        }
+        cudaGraphExecDestroy(exec);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+    }
+    enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, done, iters - done, stream, &rc);
+    if (rc) return rc;
+    if (iters & 1)
+        NLSB_CUDA(cudaMemcpyAsync(psi, work, sizeof(double2) * (size_t)batch * rows * cols, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+// 0 = automatic (fused), 1 = per-stage kernels, 2 = fused step kernel
+static std::atomic<int> g_path_2d{0};
+
+int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
+                          const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream);
+
 int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                    const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
+{
+    if (g_path_2d.load() == 1)
+        return enqueue_rk4_2d_staged(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
+    return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
+}
+
+int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
+                          const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
 {
     int rc = 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -138,9 +207,13 @@ int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double d
     if (cap == cudaStreamCaptureStatusNone && iters >= 2 * chunk) {
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
-        NLSB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        for (int s = 0; s < chunk; ++s) enqueue_step_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, stream, &rc);
-        cudaError_t e = cudaStreamEndCapture(stream, &graph);
+        // record on a private stream (the caller's may be the legacy default stream, which cannot
+        // capture); the instantiated graph is then launched on the caller's stream
+        cudaStream_t rec;
+        NLSB_TRY(internal_stream(&rec));
+        NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
+        for (int s = 0; s < chunk; ++s) enqueue_step_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, rec, &rc);
+        cudaError_t e = cudaStreamEndCapture(rec, &graph);
         if (rc) {
             if (graph) cudaGraphDestroy(graph);
             return rc;
@@ -287,6 +360,13 @@ extern "C" {
 const char *nlsb_last_error(void) { return g_error; }
 
 unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nlsb_set_2d_path(int path)
+{
+    if (path < 0 || path > 2) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2 (fused step)");
+    g_path_2d.store(path);
+    return 0;
+}
 
 int nlsb_device_available(void)
 {

@@ -38,6 +38,18 @@ struct Stage2DArgs {
     double dt6;             // dt/6
 };
 int launch_stage_2d(int order, StageMode mode, const CrossWeights &w, const Stage2DArgs &a, cudaStream_t stream);
+// fused_2d.cu: one launch advances psi by one full RK4 step (in -> out, distinct buffers).
+struct Fused2DStep {
+    int batch, rows, cols;   // local arrays are [batch][rows][cols]
+    int grow0, grows;        // global row of local row 0 and global row count (slab decomposition; else 0, rows)
+    int out_row0, out_row1;  // local rows to produce
+    const double2 *in;
+    double2 *out;
+    const double *pumping;
+    const double *coeffs;    // [batch][23]
+    double dt;
+};
+int launch_rk4_step_fused_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
 int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
                            double sign, cudaStream_t stream);
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,

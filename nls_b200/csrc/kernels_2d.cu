@@ -109,7 +109,8 @@ __global__ void reservoir_kernel(size_t npts, RhsCoeffs c, const double *__restr
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts; t += stride)
-        r[t] = c.c12 * pumping[t] / (c.c13 + c.c14 * u_sqr[t]);   // nls.f90:580 / :838
+        // nls.f90:580 / :838, each operation rounded separately as in the reference (no contraction)
+        r[t] = __ddiv_rn(__dmul_rn(c.c12, pumping[t]), __dadd_rn(c.c13, __dmul_rn(c.c14, u_sqr[t])));
 }
 
 template <int K>

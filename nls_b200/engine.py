@@ -41,6 +41,12 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def set_2d_path(path):
+    """Select the 2D kernels: "auto" / "fused" (one launch per RK step) or "staged" (one per RK stage)."""
+    code = {"auto": 0, "staged": 1, "fused": 2}[path]
+    _lib.call("nlsb_set_2d_path", code)
+
+
 def radial_taps(n, order, dx):
     """Row-major tap table of the radial operator (host, float64, bit-identical to make_laplacian)."""
     taps = np.zeros((n, order), dtype=np.float64)
@@ -61,13 +67,13 @@ def _coeff_table(coeffs, batch):
         c = np.broadcast_to(c, (batch, 23))
     if c.shape != (batch, 23):
         raise ValueError("coeffs must have shape (23,) or (batch, 23); got %r" % (c.shape,))
-    return np.ascontiguousarray(c)
+    return np.array(c, dtype=np.float64, order="C", copy=True)
 
 
 def _to_device(a, dtype, device):
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+    return torch.from_numpy(np.array(a, order="C", copy=True)).to(device=device, dtype=dtype)
 
 
 class Ensemble1D(object):

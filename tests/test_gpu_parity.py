@@ -147,14 +147,38 @@ def test_runge_kutta_with_caller_supplied_band(nls):
     assert rel_l2(got, want) <= 1e-10
 
 
-@pytest.mark.parametrize("order,n,iters", [(3, 40, 300), (5, 7, 50), (5, 96, 500), (5, 129, 200), (7, 64, 300)])
-def test_solve_2d(nls, order, n, iters):
+@pytest.fixture(params=["fused", "staged"])
+def path_2d(request):
+    """Both 2D implementations (fused whole-step kernel, per-stage kernels) are held to the same bar."""
+    from nls_b200.engine import set_2d_path
+    set_2d_path(request.param)
+    yield request.param
+    set_2d_path("auto")
+
+
+@pytest.mark.parametrize("order,n,iters", [(3, 40, 300), (5, 7, 50), (5, 96, 501), (5, 129, 200), (7, 64, 300),
+                                           (3, 3, 20), (7, 7, 33), (5, 31, 65), (7, 100, 64), (3, 257, 40)])
+def test_solve_2d(nls, path_2d, order, n, iters):
     m = model_2d(n, iters, order=order, radius=min(10.0, n * 0.1 / 4))
-    args = (m.dt, m.dx, order, iters, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    args = (m.dt, m.dx, order, iters, m.getPumping(), m.getCoefficients(), rough_field((n, n), n) * 0.05 + 0.1)
     want = O.dp.solve_nls_2d(*args)
     got = nls.solve_nls_2d(*args)
     assert got.shape == (n, n) and got.dtype == np.complex128
     assert rel_l2(got, want) <= 1e-10
+
+
+def test_fused_and_staged_paths_agree(nls):
+    from nls_b200.engine import set_2d_path
+    m = model_2d(200, 300)
+    args = (m.dt, m.dx, 5, 300, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+    try:
+        set_2d_path("staged")
+        a = nls.solve_nls_2d(*args)
+        set_2d_path("fused")
+        b = nls.solve_nls_2d(*args)
+    finally:
+        set_2d_path("auto")
+    assert rel_l2(a, b) <= 1e-13
 
 
 def test_solve_2d_nonsymmetric_input_keeps_index_convention(nls):
