@@ -153,13 +153,16 @@ int nlsb_dev_band_matvec_1d(int n, int order, const double *taps, const double *
 
 /* Batched 2D grids of rows x cols points (cols contiguous).  wx, wy: HOST arrays of `order` weights.
  * pumping: [batch][rows][cols]; coeffs: DEVICE [batch][23]; psi: [batch][rows][cols] complex, in place.
+ * shared_coeffs_host: HOST copy of the 23 coefficients when every member uses the same ones (lets the
+ * kernel read them from its constant bank), else NULL.
  * workspace: device scratch of nlsb_dev_rk4_2d_workspace() bytes. */
 size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols);
 /* Which kernels advance 2D grids: 0 = automatic (the fused whole-step kernel), 1 = one launch per RK
  * stage, 2 = fused.  Both give the same result to rounding; the switch exists for tests and profiling. */
 int nlsb_set_2d_path(int path);
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
-                    const double *wy, const double *pumping, const double *coeffs, double *psi,
+                    const double *wy, const double *pumping, const double *coeffs,
+                    const double *shared_coeffs_host, double *psi,
                     void *workspace, size_t workspace_bytes, nlsb_stream_t stream);
 int nlsb_dev_hamiltonian_2d(int batch, int rows, int cols, int order, const double *wx, const double *wy,
                             const double *pumping, const double *coeffs, const double *u, double *v,

@@ -127,17 +127,35 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
     stage(kStageLast, ya, psi, 0.0);
 }
 
+// 0 = automatic (fused 32x32), 1 = per-stage kernels, 2 = fused 32x32 tiles, 3 = fused 32x64 tiles
+static std::atomic<int> g_path_2d{0};
+
+// Coefficients shared by every member of the batch (host copy), or null: set by the entry points that
+// know them so that the fused kernel can read them from its constant bank.
+static thread_local const RhsCoeffs *g_uniform_coeffs = nullptr;
+struct UniformCoeffsScope {
+    RhsCoeffs value;
+    explicit UniformCoeffsScope(const double *coeffs23_host)
+    {
+        if (coeffs23_host) {
+            value = rhs_coeffs_from(coeffs23_host);
+            g_uniform_coeffs = &value;
+        }
+    }
+    ~UniformCoeffsScope() { g_uniform_coeffs = nullptr; }
+};
+
 // Fused path: one launch per RK step, psi ping-pongs between `psi` and the first plane of `work`.
 void enqueue_fused_steps_2d(int batch, int rows, int cols, int order, double dt, const CrossWeights &w,
                             const double *pumping, const double *coeffs, double2 *psi, double2 *work, int first_step,
                             int nsteps, cudaStream_t stream, int *rc)
 {
-    Fused2DStep s{batch, rows, cols, 0, rows, 0, rows, nullptr, nullptr, pumping, coeffs, dt};
+    Fused2DStep s{batch, rows, cols, 0, rows, 0, rows, nullptr, nullptr, pumping, coeffs, dt, g_uniform_coeffs};
     for (int i = 0; i < nsteps; ++i) {
         const bool even = ((first_step + i) & 1) == 0;
         s.in = even ? psi : work;
         s.out = even ? work : psi;
-        int r = launch_rk4_step_fused_2d(order, s, w, stream);
+        int r = launch_rk4_step_fused_2d(order, g_path_2d.load() == 3 ? 1 : 0, s, w, stream);
         if (r && !*rc) *rc = r;
     }
 }
@@ -181,9 +199,6 @@ int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, do
         NLSB_CUDA(cudaMemcpyAsync(psi, work, sizeof(double2) * (size_t)batch * rows * cols, cudaMemcpyDeviceToDevice, stream));
     return 0;
 }
-
-// 0 = automatic (fused), 1 = per-stage kernels, 2 = fused step kernel
-static std::atomic<int> g_path_2d{0};
 
 int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                           const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream);
@@ -280,6 +295,7 @@ int host_rk4_2d(double dt, const CrossWeights &w, int n, int order, int iters, c
     NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
     NLSB_TRY(mem.upload(&d_psi, reinterpret_cast<const double2 *>(u0), np));
     NLSB_TRY(mem.alloc(&d_work, 3 * np));
+    UniformCoeffsScope uniform(coeffs);
     NLSB_TRY(enqueue_rk4_2d(1, n, n, order, iters, dt, w, d_p, d_c, d_psi, d_work, s));
     NLSB_CUDA(cudaMemcpyAsync(u, d_psi, sizeof(double2) * np, cudaMemcpyDeviceToHost, s));
     NLSB_CUDA(cudaStreamSynchronize(s));
@@ -363,7 +379,7 @@ unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memo
 
 int nlsb_set_2d_path(int path)
 {
-    if (path < 0 || path > 2) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2 (fused step)");
+    if (path < 0 || path > 3) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage), 2 or 3 (fused step)");
     g_path_2d.store(path);
     return 0;
 }
@@ -673,9 +689,10 @@ size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols)
 }
 
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
-                    const double *wy, const double *pumping, const double *coeffs, double *psi, void *workspace,
-                    size_t workspace_bytes, nlsb_stream_t stream)
+                    const double *wy, const double *pumping, const double *coeffs, const double *shared_coeffs_host,
+                    double *psi, void *workspace, size_t workspace_bytes, nlsb_stream_t stream)
 {
+    UniformCoeffsScope uniform(shared_coeffs_host);
     if (!pumping || !coeffs || !psi || !workspace || batch < 1 || iters < 0) return fail(NLSB_EINVAL, "dev_rk4_2d: bad arguments");
     NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
     if (workspace_bytes < nlsb_dev_rk4_2d_workspace(batch, rows, cols))

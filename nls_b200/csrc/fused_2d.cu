@@ -11,14 +11,15 @@
 // and writes the tile of the new psi once.  The kernel is then bounded by the FP64 pipe and the
 // shared-memory crossbar, not by HBM (DESIGN.md "fused step").
 //
-// Data layout in shared memory: three frames (B0 = psi, B1, B2 = stage inputs, ping-pong) of
-// W x H nodes stored as separate re / im planes of doubles, plus one plane of c12*P.  A thread
-// works on micro-tiles of 2 (x) x 4 (y) nodes: with the planar layout a 16-byte LDS/STS moves the
-// same component of two x-adjacent nodes, consecutive lanes touch consecutive 16-byte words
-// (conflict-free), and a micro-tile needs 4 loads per node and stage instead of 9.
-// The first 256 micro-tiles of every stage's work list are the tile itself, always mapped to the
-// same thread, so the RK accumulator of a node lives in that thread's registers across stages;
-// the halo-ring micro-tiles follow in the list and carry no state.
+// Shared memory: frame B0 = psi on tile + 4K halo; B1, B2 = stage inputs on the owned region
+// (tile + 3K), ping-pong; CP = c12*P on the owned region.  Every field is stored as separate re / im
+// planes of doubles, so one 16-byte LDS/STS moves the same component of two x-adjacent nodes and
+// consecutive lanes touch consecutive 16-byte words.  A thread works on micro-tiles of 2 (x) x MB (y)
+// nodes, which cuts the stencil's shared-memory loads from 9 to 5 per node (MB = 2, order 5).
+// Work list of a stage: first the tile's own micro-tiles -- one per thread, the same thread in
+// every stage, so psi, c12*P and the RK accumulator of those nodes stay in registers for the whole
+// step -- then the micro-tiles of the halo ring of that stage (top band, bottom band, left and
+// right columns), which carry no state and are dealt round-robin.
 //
 // Outside the square the field is identically zero at every stage (the reference's truncated
 // band matrix): out-of-domain nodes are forced to zero after each stage.  Every node's value is
@@ -32,33 +33,34 @@ namespace nlsb {
 
 namespace {
 
-constexpr int kFusedThreads = 256;
+constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-template <int K_>
+template <int K_, int TY_, int MB_, int THREADS_, int MINBLOCKS_>
 struct FusedCfg {
-    static constexpr int K = K_;
+    static constexpr int K = K_, TY = TY_, MB = MB_, THREADS = THREADS_, MINBLOCKS = MINBLOCKS_;
     static constexpr int TX = 32;
-    static constexpr int TY = (K_ == 3) ? 32 : 64;
     static constexpr int PH = (K_ + 1) / 2;              // x-neighbour pairs on each side
     static constexpr int HXL = 4 * K_ + 2 * (K_ & 1);    // frame columns left of the tile (even)
     static constexpr int OX = HXL - 3 * K_ - (K_ & 1);   // first owned column (even, <= tile - 3K)
-    static constexpr int W = TX + 2 * HXL;               // frame width (even)
+    static constexpr int W0 = TX + 2 * HXL;              // frame width (even)
     static constexpr int NMX = (HXL + TX + 3 * K_ - OX + 1) / 2;   // micro-tiles per row of the owned region
-    static constexpr int DY = 4 * ((3 * K_ + 3) / 4);    // owned rows above the tile (multiple of 4)
+    static constexpr int DY = MB_ * cdiv(3 * K_, MB_);   // owned rows above the tile (multiple of MB)
     static constexpr int OY = K_;                        // first owned row
     static constexpr int FY0 = OY + DY;                  // first tile row
-    static constexpr int NMY = DY / 4 + TY / 4 + (3 * K_ + 3) / 4;
-    static constexpr int H = OY + 4 * NMY + K_;          // frame height
-    static constexpr int PLANE = W * H;                  // doubles per plane
-    static constexpr int NPLANES = 7;                    // 3 frames x (re, im) + c12*P
-    static constexpr size_t SMEM = sizeof(double) * PLANE * NPLANES;
-    static constexpr int TMX0 = (HXL - OX) / 2;          // first tile micro-tile column
-    static constexpr int TMY0 = DY / 4;
-    static constexpr int TMW = TX / 2, TMH = TY / 4;
+    static constexpr int NMY = DY / MB_ + TY_ / MB_ + cdiv(3 * K_, MB_);
+    static constexpr int H0 = OY + MB_ * NMY + K_;       // frame height
+    static constexpr int W1 = 2 * NMX, H1 = MB_ * NMY;   // owned region
+    static constexpr int PLANE0 = W0 * H0, PLANE1 = W1 * H1;
+    static constexpr size_t SMEM = sizeof(double) * (2 * PLANE0 + 5 * PLANE1);
+    static constexpr int TMX0 = (HXL - OX) / 2;          // first tile micro-tile column / row
+    static constexpr int TMY0 = DY / MB_;
+    static constexpr int TMW = TX / 2, TMH = TY_ / MB_;
     static constexpr int NTILE = TMW * TMH;
-    static_assert(OX % 2 == 0 && W % 2 == 0, "pairs must be 16-byte aligned");
-    static_assert(OX >= 2 * PH && OX + 2 * NMX + 2 * PH <= W, "x halo of the frame too small");
-    static_assert(SMEM <= 227 * 1024, "frame does not fit in shared memory");
+    static_assert(TY_ % MB_ == 0, "tile height must be a multiple of the micro-tile height");
+    static_assert(NTILE == THREADS_, "one tile micro-tile per thread");
+    static_assert(OX % 2 == 0 && W0 % 2 == 0, "pairs must be 16-byte aligned");
+    static_assert(OX >= 2 * PH && OX + 2 * NMX + 2 * PH <= W0, "x halo of the frame too small");
+    static_assert(SMEM <= 227 * 1024, "frames do not fit in shared memory");
 };
 
 struct FusedArgs {
@@ -69,40 +71,35 @@ struct FusedArgs {
     const double2 *in;       // [batch][rows][cols]
     double2 *out;            // [batch][rows][cols]
     const double *pumping;   // [batch][rows][cols]
-    const double *coeffs;    // [batch][23]
-    double dt;
+    const double *coeffs;    // [batch][23] (per-member coefficients) -- unused when UNIFORM
+    RhsCoeffs cu;            // coefficients shared by every member (UNIFORM kernels read them from the
+                             // constant bank instead of pinning 14 registers)
+    double dt, half_dt, dt6;
 };
 
 __device__ __forceinline__ double2 lds2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ void sts2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
 
-// Micro-tile `idx` of stage S (1-based): tile micro-tiles first, then the halo ring of the stage
-// enumerated as top band, bottom band, left columns, right columns.
+// Ring micro-tile `idx` (0-based, after the tile's own micro-tiles) of stage S (1-based).
 template <typename C, int S>
 struct StageGrid {
     static constexpr int E = (4 - S) * C::K;
     static constexpr int MX0 = (C::HXL - E - C::OX) / 2;
     static constexpr int MX1 = (C::HXL + C::TX + E - C::OX + 1) / 2;
-    static constexpr int MY0 = (C::FY0 - E - C::OY) / 4;
-    static constexpr int MY1 = (C::FY0 + C::TY + E - C::OY + 3) / 4;
+    static constexpr int MY0 = (C::FY0 - E - C::OY) / C::MB;
+    static constexpr int MY1 = (C::FY0 + C::TY + E - C::OY + C::MB - 1) / C::MB;
     static constexpr int GW = MX1 - MX0;
     static constexpr int NTOP = GW * (C::TMY0 - MY0);
     static constexpr int NBOT = GW * (MY1 - (C::TMY0 + C::TMH));
     static constexpr int LW = C::TMX0 - MX0;
     static constexpr int RW = MX1 - (C::TMX0 + C::TMW);
-    static constexpr int NLEFT = LW * C::TMH;
-    static constexpr int NRIGHT = RW * C::TMH;
-    static constexpr int COUNT = C::NTILE + NTOP + NBOT + NLEFT + NRIGHT;
+    static constexpr int SW = LW + RW;                  // left and right columns of one micro-row side by side
+    static constexpr int NSIDE = SW * C::TMH;
+    static constexpr int NRING = NTOP + NBOT + NSIDE;
     static_assert(MX0 >= 0 && MX1 <= C::NMX && MY0 >= 0 && MY1 <= C::NMY, "stage region leaves the owned region");
 
     __device__ static __forceinline__ void locate(int idx, int &mx, int &my)
     {
-        if (idx < C::NTILE) {
-            mx = C::TMX0 + idx % C::TMW;
-            my = C::TMY0 + idx / C::TMW;
-            return;
-        }
-        idx -= C::NTILE;
         if (idx < NTOP) {
             mx = MX0 + idx % GW;
             my = MY0 + idx / GW;
@@ -115,60 +112,80 @@ struct StageGrid {
             return;
         }
         idx -= NBOT;
-        if (idx < NLEFT) {
-            mx = MX0 + idx % (LW > 0 ? LW : 1);
-            my = C::TMY0 + idx / (LW > 0 ? LW : 1);
-            return;
-        }
-        idx -= NLEFT;
-        mx = C::TMX0 + C::TMW + idx % (RW > 0 ? RW : 1);
-        my = C::TMY0 + idx / (RW > 0 ? RW : 1);
+        constexpr int sw = SW > 0 ? SW : 1;
+        const int c = idx % sw;
+        my = C::TMY0 + idx / sw;
+        mx = c < LW ? MX0 + c : C::TMX0 + C::TMW + (c - LW);
     }
 };
 
 template <typename C>
 struct Smem {
-    double *plane;
-    __device__ __forceinline__ double *re(int frame) const { return plane + (2 * frame) * C::PLANE; }
-    __device__ __forceinline__ double *im(int frame) const { return plane + (2 * frame + 1) * C::PLANE; }
-    __device__ __forceinline__ double *cp() const { return plane + 6 * C::PLANE; }
+    double *base;
+    // frame 0 (psi): pitch W0; frames 1, 2 and cp: owned region, pitch W1
+    __device__ __forceinline__ double *re0() const { return base; }
+    __device__ __forceinline__ double *im0() const { return base + C::PLANE0; }
+    __device__ __forceinline__ double *re(int f) const { return base + 2 * C::PLANE0 + (2 * (f - 1)) * C::PLANE1; }
+    __device__ __forceinline__ double *im(int f) const { return base + 2 * C::PLANE0 + (2 * (f - 1) + 1) * C::PLANE1; }
+    __device__ __forceinline__ double *cp() const { return base + 2 * C::PLANE0 + 4 * C::PLANE1; }
 };
 
 struct TileCtx {
     int x0, y0;          // local array coordinates of frame node (0, 0)
-    int rows, cols, grow0, grows;
+    int cols, grow0, grows;
     int out_row0, out_row1;
     double half_dt, dt, dt6;
 };
 
-// One micro-tile of stage S.  src/dst: frame indices of the stage input / next stage input.
-template <typename C, int S, bool WITH_ACC>
+// Per-thread state of the tile micro-tile a thread owns for the whole step.
+template <int MB>
+struct Owned {
+    double ure[MB][2], uim[MB][2], cp[MB][2];
+    double yre[MB][2], yim[MB][2];   // the stage input at the owned nodes (what this thread stored last stage)
+    double2 acc[MB][2];
+};
+
+// One micro-tile of stage S.  OWNED: the thread's own tile micro-tile (state in registers,
+// writes the new psi in stage 4); otherwise a stateless ring micro-tile.
+template <typename C, int S, bool OWNED>
 __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, const RhsCoeffs &c,
                                            const double (&wx)[2 * C::K + 1], const double (&wy)[2 * C::K + 1],
-                                           int mx, int my, bool is_tile, double2 (&acc)[4][2], double2 *__restrict__ out)
+                                           int mx, int my, Owned<C::MB> &own, double2 *__restrict__ out)
 {
-    constexpr int K = C::K, W = C::W, PH = C::PH;
-    constexpr int src = (S == 1) ? 0 : (S == 2) ? 1 : (S == 3) ? 2 : 1;
-    constexpr int dst = (S == 1) ? 1 : (S == 2) ? 2 : 1;
-    const int fx = C::OX + 2 * mx, fy = C::OY + 4 * my;
-    const double *sre = sm.re(src), *sim = sm.im(src);
+    constexpr int K = C::K, PH = C::PH, MB = C::MB;
+    // stage input: S=1 psi frame; S=2 frame 1; S=3 frame 2; S=4 frame 1.  Output: 1, 2, 1.
+    constexpr int SRC = (S == 1) ? 0 : (S == 3) ? 2 : 1;
+    constexpr int DST = (S == 2) ? 2 : 1;
+    constexpr int WS = (SRC == 0) ? C::W0 : C::W1;
+    const int fx = C::OX + 2 * mx, fy = C::OY + MB * my;     // frame coordinates
+    const int o1 = (MB * my) * C::W1 + 2 * mx;                 // offset in owned-region planes
+    const double *sre = (SRC == 0) ? sm.re0() : sm.re(SRC);
+    const double *sim = (SRC == 0) ? sm.im0() : sm.im(SRC);
+    const int os = (SRC == 0) ? fy * C::W0 + fx : o1;
 
-    double lre[4][2], lim[4][2], cre[4][2], cim[4][2];
+    double lre[MB][2], lim[MB][2], cre[MB][2], cim[MB][2];
 #pragma unroll
-    for (int r = -K; r < 4 + K; ++r) {
-        const int o = (fy + r) * W + fx;
-        const double2 vr = lds2(sre + o), vi = lds2(sim + o);
-        if (r >= 0 && r < 4) {
+    for (int r = -K; r < MB + K; ++r) {
+        const int o = os + r * WS;
+        double2 vr, vi;
+        if (OWNED && S > 1 && r >= 0 && r < MB) {
+            // the centre pair of an owned row is what this thread wrote itself one stage ago
+            vr = make_double2(own.yre[r][0], own.yre[r][1]);
+            vi = make_double2(own.yim[r][0], own.yim[r][1]);
+        } else {
+            vr = lds2(sre + o);
+            vi = lds2(sim + o);
+        }
+        if (r >= 0 && r < MB) {
             cre[r][0] = vr.x; cre[r][1] = vr.y;
             cim[r][0] = vi.x; cim[r][1] = vi.y;
         }
         // scatter input row r into the output rows it touches: output row j receives, in this order,
         // the taps of the K rows above it, its own row (x taps and centre), the K rows below it
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < MB; ++j) {
             const int d = r - j;               // input row = output row + d
             if (d == 0) {
-                // x direction (includes the centre weight)
                 double xr[2 * (2 * PH + 1)], xi[2 * (2 * PH + 1)];
 #pragma unroll
                 for (int q = -PH; q <= PH; ++q) {
@@ -184,8 +201,7 @@ __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, 
                 }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    // rows j-K .. j-1 have already contributed (r starts at -K), so lre/lim are initialised
-                    double ar = lre[j][i], ai = lim[j][i];
+                    double ar = lre[j][i], ai = lim[j][i];   // rows j-K .. j-1 have already contributed
 #pragma unroll
                     for (int tp = -K; tp <= K; ++tp) {
                         ar = fma(wx[tp + K], xr[2 * PH + i + tp], ar);
@@ -212,54 +228,67 @@ __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, 
     }
 
     // pointwise part, stage algebra, domain mask
-    const double *ure = sm.re(0), *uim = sm.im(0), *cpp = sm.cp();
-    double *dre = sm.re(dst), *dim_ = sm.im(dst);
+    double *dre = sm.re(DST), *dim_ = sm.im(DST);
     const int gx = t.x0 + fx;
     const bool colin0 = gx >= 0 && gx < t.cols, colin1 = gx + 1 >= 0 && gx + 1 < t.cols;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int o = (fy + j) * W + fx;
+    for (int j = 0; j < MB; ++j) {
         const int ly = t.y0 + fy + j;
         const int gy = ly + t.grow0;
         const bool rowin = gy >= 0 && gy < t.grows;
-        const double2 cpv = lds2(cpp + o);
-        double2 ur, ui;
-        if (S == 1) {
-            ur = make_double2(cre[j][0], cre[j][1]);
-            ui = make_double2(cim[j][0], cim[j][1]);
+        double u_re[2], u_im[2], cpv[2];
+        if (OWNED) {
+            if (S == 1) {
+                const double2 p = lds2(sm.cp() + o1 + j * C::W1);
+                own.cp[j][0] = p.x; own.cp[j][1] = p.y;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { own.ure[j][i] = cre[j][i]; own.uim[j][i] = cim[j][i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { u_re[i] = own.ure[j][i]; u_im[i] = own.uim[j][i]; cpv[i] = own.cp[j][i]; }
         } else {
-            ur = lds2(ure + o);
-            ui = lds2(uim + o);
+            const double2 p = lds2(sm.cp() + o1 + j * C::W1);
+            cpv[0] = p.x; cpv[1] = p.y;
+            if (S == 1) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { u_re[i] = cre[j][i]; u_im[i] = cim[j][i]; }
+            } else {
+                const int o0 = (fy + j) * C::W0 + fx;
+                const double2 a = lds2(sm.re0() + o0), b = lds2(sm.im0() + o0);
+                u_re[0] = a.x; u_re[1] = a.y; u_im[0] = b.x; u_im[1] = b.y;
+            }
         }
         double yr[2], yi[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const double2 y = make_double2(cre[j][i], cim[j][i]);
-            const double2 k = rhs_point(c, i ? cpv.y : cpv.x, y, lre[j][i], lim[j][i]);
-            const double u_re = i ? ur.y : ur.x, u_im = i ? ui.y : ui.x;
+            const double2 k = rhs_point(c, cpv[i], make_double2(cre[j][i], cim[j][i]), lre[j][i], lim[j][i]);
             const bool inside = rowin && (i ? colin1 : colin0);
             if (S < 4) {
                 const double cy = (S == 3) ? t.dt : t.half_dt;
-                yr[i] = inside ? fma(k.x, cy, u_re) : 0.0;
-                yi[i] = inside ? fma(k.y, cy, u_im) : 0.0;
+                yr[i] = inside ? fma(k.x, cy, u_re[i]) : 0.0;
+                yi[i] = inside ? fma(k.y, cy, u_im[i]) : 0.0;
             }
-            if (WITH_ACC) {
+            if (OWNED) {
                 if (S == 1) {
-                    acc[j][i] = k;
+                    own.acc[j][i] = k;
                 } else if (S < 4) {
-                    acc[j][i].x = fma(2.0, k.x, acc[j][i].x);
-                    acc[j][i].y = fma(2.0, k.y, acc[j][i].y);
+                    own.acc[j][i].x = fma(2.0, k.x, own.acc[j][i].x);
+                    own.acc[j][i].y = fma(2.0, k.y, own.acc[j][i].y);
                 } else {
-                    yr[i] = fma(acc[j][i].x + k.x, t.dt6, u_re);
-                    yi[i] = fma(acc[j][i].y + k.y, t.dt6, u_im);
+                    yr[i] = fma(own.acc[j][i].x + k.x, t.dt6, u_re[i]);
+                    yi[i] = fma(own.acc[j][i].y + k.y, t.dt6, u_im[i]);
                 }
             }
         }
         if (S < 4) {
-            sts2(dre + o, yr[0], yr[1]);
-            sts2(dim_ + o, yi[0], yi[1]);
-        } else if (WITH_ACC) {
-            if (is_tile && rowin && ly >= t.out_row0 && ly < t.out_row1) {
+            sts2(dre + o1 + j * C::W1, yr[0], yr[1]);
+            sts2(dim_ + o1 + j * C::W1, yi[0], yi[1]);
+            if (OWNED) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { own.yre[j][i] = yr[i]; own.yim[j][i] = yi[i]; }
+            }
+        } else if (OWNED) {
+            if (rowin && ly >= t.out_row0 && ly < t.out_row1) {
                 double2 *q = out + (size_t)ly * t.cols + gx;
                 if (colin0) q[0] = make_double2(yr[0], yi[0]);
                 if (colin1) q[1] = make_double2(yr[1], yi[1]);
@@ -271,21 +300,16 @@ __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, 
 template <typename C, int S>
 __device__ __forceinline__ void run_stage(const Smem<C> &sm, const TileCtx &t, const RhsCoeffs &c,
                                           const double (&wx)[2 * C::K + 1], const double (&wy)[2 * C::K + 1],
-                                          double2 (&acc)[4][2], double2 *__restrict__ out)
+                                          Owned<C::MB> &own, double2 *__restrict__ out)
 {
     using G = StageGrid<C, S>;
     const int tid = threadIdx.x;
-    int mx, my;
-    // round 0: the tile's own micro-tiles (fixed thread mapping, carries the RK accumulator)
-    if (tid < G::COUNT) {
-        G::locate(tid, mx, my);
-        micro_tile<C, S, true>(sm, t, c, wx, wy, mx, my, tid < C::NTILE, acc, out);
-    }
+    micro_tile<C, S, true>(sm, t, c, wx, wy, C::TMX0 + tid % C::TMW, C::TMY0 + tid / C::TMW, own, out);
     if (S < 4) {
-        double2 none[4][2];
-        for (int idx = tid + kFusedThreads; idx < G::COUNT; idx += kFusedThreads) {
+        for (int idx = tid; idx < G::NRING; idx += C::THREADS) {
+            int mx, my;
             G::locate(idx, mx, my);
-            micro_tile<C, S, false>(sm, t, c, wx, wy, mx, my, false, none, out);
+            micro_tile<C, S, false>(sm, t, c, wx, wy, mx, my, own, out);
         }
     }
 }
@@ -296,12 +320,11 @@ struct WeightsArg {
     double wy[2 * K + 1];
 };
 
-template <int K>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-rk4_step_fused_kernel(FusedArgs a, WeightsArg<K> wa)
+template <typename C, bool UNIFORM>
+__global__ void __launch_bounds__(C::THREADS, C::MINBLOCKS)
+rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ WeightsArg<C::K> wa)
 {
-    using C = FusedCfg<K>;
-    static_assert(C::NTILE <= kFusedThreads, "tile micro-tiles must fit one round");
+    constexpr int K = C::K;
     extern __shared__ __align__(16) double smem_raw[];
     Smem<C> sm{smem_raw};
 
@@ -312,63 +335,101 @@ rk4_step_fused_kernel(FusedArgs a, WeightsArg<K> wa)
     const double2 *__restrict__ in = a.in + member * plane;
     double2 *__restrict__ out = a.out + member * plane;
     const double *__restrict__ P = a.pumping + member * plane;
-    const RhsCoeffs c = load_rhs_coeffs(a.coeffs + member * 23);
+    const RhsCoeffs c = UNIFORM ? a.cu : load_rhs_coeffs(a.coeffs + member * 23);
 
     TileCtx t;
     t.x0 = tile_x * C::TX - C::HXL;
     t.y0 = a.out_row0 + tile_y * C::TY - C::FY0;
-    t.rows = a.rows; t.cols = a.cols; t.grow0 = a.grow0; t.grows = a.grows;
+    t.cols = a.cols; t.grow0 = a.grow0; t.grows = a.grows;
     t.out_row0 = a.out_row0; t.out_row1 = a.out_row1;
-    t.half_dt = a.dt / 2; t.dt = a.dt; t.dt6 = a.dt / 6;
+    t.half_dt = a.half_dt; t.dt = a.dt; t.dt6 = a.dt6;
 
     double wx[2 * K + 1], wy[2 * K + 1];
 #pragma unroll
     for (int i = 0; i < 2 * K + 1; ++i) { wx[i] = wa.wx[i]; wy[i] = wa.wy[i]; }
 
-    // ---- fill: psi frame (zero outside the local array / the domain) and c12*P ----------------
+    // ---- fill: psi frame (zero outside the local array / the domain), loads batched 4 deep -------
     {
-        double *b0r = sm.re(0), *b0i = sm.im(0), *cpp = sm.cp();
-        constexpr int PAIRS = C::W / 2;
-        for (int i = tid; i < PAIRS * C::H; i += kFusedThreads) {
-            const int fy = i / PAIRS, fx = 2 * (i % PAIRS);
-            const int lx = t.x0 + fx, ly = t.y0 + fy;
-            const int gy = ly + t.grow0;
-            const bool rowok = ly >= 0 && ly < t.rows && gy >= 0 && gy < t.grows;
-            double2 v0 = make_double2(0.0, 0.0), v1 = v0;
-            double p0 = 0.0, p1 = 0.0;
-            if (rowok) {
-                const size_t g = (size_t)ly * t.cols + lx;
-                if (lx >= 0 && lx < t.cols) { v0 = in[g]; p0 = c.c12 * P[g]; }
-                if (lx + 1 >= 0 && lx + 1 < t.cols) { v1 = in[g + 1]; p1 = c.c12 * P[g + 1]; }
+        double *b0r = sm.re0(), *b0i = sm.im0();
+        constexpr int PAIRS = C::W0 / 2, TOTAL = PAIRS * C::H0, UNROLL = 4;
+        for (int base = tid; base < TOTAL; base += UNROLL * C::THREADS) {
+            double2 v0[UNROLL], v1[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int i = base + u * C::THREADS;
+                v0[u] = make_double2(0.0, 0.0);
+                v1[u] = v0[u];
+                if (i < TOTAL) {
+                    const int fy = i / PAIRS, fx = 2 * (i % PAIRS);
+                    const int lx = t.x0 + fx, ly = t.y0 + fy, gy = ly + t.grow0;
+                    if (ly >= 0 && ly < a.rows && gy >= 0 && gy < t.grows) {
+                        const double2 *g = in + (size_t)ly * t.cols + lx;
+                        if (lx >= 0 && lx < t.cols) v0[u] = g[0];
+                        if (lx + 1 >= 0 && lx + 1 < t.cols) v1[u] = g[1];
+                    }
+                }
             }
-            const int o = fy * C::W + fx;
-            sts2(b0r + o, v0.x, v1.x);
-            sts2(b0i + o, v0.y, v1.y);
-            sts2(cpp + o, p0, p1);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int i = base + u * C::THREADS;
+                if (i < TOTAL) {
+                    const int o = (i / PAIRS) * C::W0 + 2 * (i % PAIRS);
+                    sts2(b0r + o, v0[u].x, v1[u].x);
+                    sts2(b0i + o, v0[u].y, v1[u].y);
+                }
+            }
+        }
+        // c12*P on the owned region
+        double *cpp = sm.cp();
+        constexpr int PAIRS1 = C::W1 / 2, TOTAL1 = PAIRS1 * C::H1;
+        for (int base = tid; base < TOTAL1; base += UNROLL * C::THREADS) {
+            double p0[UNROLL], p1[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int i = base + u * C::THREADS;
+                p0[u] = 0.0; p1[u] = 0.0;
+                if (i < TOTAL1) {
+                    const int ry = i / PAIRS1, rx = 2 * (i % PAIRS1);
+                    const int lx = t.x0 + C::OX + rx, ly = t.y0 + C::OY + ry, gy = ly + t.grow0;
+                    if (ly >= 0 && ly < a.rows && gy >= 0 && gy < t.grows) {
+                        const double *g = P + (size_t)ly * t.cols + lx;
+                        if (lx >= 0 && lx < t.cols) p0[u] = g[0];
+                        if (lx + 1 >= 0 && lx + 1 < t.cols) p1[u] = g[1];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int i = base + u * C::THREADS;
+                if (i < TOTAL1) sts2(cpp + (i / PAIRS1) * C::W1 + 2 * (i % PAIRS1), c.c12 * p0[u], c.c12 * p1[u]);
+            }
         }
     }
     __syncthreads();
 
-    double2 acc[4][2];
-    run_stage<C, 1>(sm, t, c, wx, wy, acc, out);
+    Owned<C::MB> own;
+    run_stage<C, 1>(sm, t, c, wx, wy, own, out);
     __syncthreads();
-    run_stage<C, 2>(sm, t, c, wx, wy, acc, out);
+    run_stage<C, 2>(sm, t, c, wx, wy, own, out);
     __syncthreads();
-    run_stage<C, 3>(sm, t, c, wx, wy, acc, out);
+    run_stage<C, 3>(sm, t, c, wx, wy, own, out);
     __syncthreads();
-    run_stage<C, 4>(sm, t, c, wx, wy, acc, out);
+    run_stage<C, 4>(sm, t, c, wx, wy, own, out);
 }
 
-template <int K>
-int launch_fused_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+template <typename C, bool UNIFORM>
+int launch_fused_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
 {
-    using C = FusedCfg<K>;
+    constexpr int K = C::K;
     static bool configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(rk4_step_fused_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(rk4_step_fused_kernel<C, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(rk4_step_fused_kernel<C, UNIFORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
     }
@@ -377,25 +438,40 @@ int launch_fused_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t str
     a.out_row0 = s.out_row0; a.out_row1 = s.out_row1;
     a.tiles_x = (s.cols + C::TX - 1) / C::TX;
     a.tiles_y = (s.out_row1 - s.out_row0 + C::TY - 1) / C::TY;
-    a.in = s.in; a.out = s.out; a.pumping = s.pumping; a.coeffs = s.coeffs; a.dt = s.dt;
+    a.in = s.in; a.out = s.out; a.pumping = s.pumping; a.coeffs = s.coeffs;
+    if (UNIFORM) a.cu = *s.uniform;
+    a.dt = s.dt; a.half_dt = s.dt / 2; a.dt6 = s.dt / 6;
     if (a.tiles_x <= 0 || a.tiles_y <= 0) return 0;
     WeightsArg<K> wa;
     for (int i = 0; i < 2 * K + 1; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
     const dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)s.batch);
-    rk4_step_fused_kernel<K><<<grid, kFusedThreads, C::SMEM, stream>>>(a, wa);
+    rk4_step_fused_kernel<C, UNIFORM><<<grid, C::THREADS, C::SMEM, stream>>>(a, wa);
     count_launches(1);
     return (int)cudaGetLastError();
 }
 
+// Tile shapes.  variant 0: 32x32 tiles, 256 threads, two CTAs per SM (one CTA's fill and barriers
+// hide behind the other's arithmetic); variant 1: 32x64 tiles, 512 threads, one CTA per SM (less
+// redundant halo work).
+template <int K>
+int launch_fused_k(int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    using Small = FusedCfg<K, 32, 2, 256, (K == 3) ? 1 : 2>;
+    using Tall = FusedCfg<(K == 3) ? 2 : K, 64, 2, 512, 1>;
+    if (K == 3 || variant == 0)
+        return s.uniform ? launch_fused_cfg<Small, true>(s, w, stream) : launch_fused_cfg<Small, false>(s, w, stream);
+    return s.uniform ? launch_fused_cfg<Tall, true>(s, w, stream) : launch_fused_cfg<Tall, false>(s, w, stream);
+}
+
 }  // namespace
 
-int launch_rk4_step_fused_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
 {
     if (s.batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", s.batch);
     switch (order) {
-    case 3: return launch_fused_k<1>(s, w, stream);
-    case 5: return launch_fused_k<2>(s, w, stream);
-    case 7: return launch_fused_k<3>(s, w, stream);
+    case 3: return launch_fused_k<1>(variant, s, w, stream);
+    case 5: return launch_fused_k<2>(variant, s, w, stream);
+    case 7: return launch_fused_k<3>(variant, s, w, stream);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
 }

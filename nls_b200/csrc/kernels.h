@@ -46,10 +46,12 @@ struct Fused2DStep {
     const double2 *in;
     double2 *out;
     const double *pumping;
-    const double *coeffs;    // [batch][23]
+    const double *coeffs;    // [batch][23] on the device
     double dt;
+    const RhsCoeffs *uniform;   // host: non-null when every member shares these coefficients
 };
-int launch_rk4_step_fused_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
+// variant 0: 32x32 tiles, two CTAs per SM; variant 1: 32x64 tiles, one CTA of 512 threads per SM
+int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
 int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
                            double sign, cudaStream_t stream);
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,

@@ -43,7 +43,7 @@ def _stream():
 
 def set_2d_path(path):
     """Select the 2D kernels: "auto" / "fused" (one launch per RK step) or "staged" (one per RK stage)."""
-    code = {"auto": 0, "staged": 1, "fused": 2}[path]
+    code = {"auto": 0, "staged": 1, "fused": 2, "fused32": 2, "fused64": 3}[path]
     _lib.call("nlsb_set_2d_path", code)
 
 
@@ -136,7 +136,10 @@ class Grid2D(object):
         self.dx, self.dt, self.order, self.batch = float(dx), float(dt), int(order), int(batch)
         self.wx, self.wy = cross_weights(self.order, self.dx)
         with torch.cuda.device(self.device):
-            self.coeffs = _to_device(_coeff_table(coeffs, self.batch), torch.float64, self.device)
+            table = _coeff_table(coeffs, self.batch)
+            # members that all share one coefficient set let the kernel keep it in its constant bank
+            self.shared_coeffs = table[0].copy() if bool((table == table[0]).all()) else None
+            self.coeffs = _to_device(table, torch.float64, self.device)
             self.pumping = self._field(pumping, torch.float64)
             self.psi = self._field(u0, torch.complex128)
             nbytes = _lib.load().nlsb_dev_rk4_2d_workspace(self.batch, self.rows, self.cols)
@@ -160,7 +163,8 @@ class Grid2D(object):
     def advance(self, iters):
         with torch.cuda.device(self.device):
             _lib.call("nlsb_dev_rk4_2d", self.batch, self.rows, self.cols, self.order, int(iters), self.dt,
-                      self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi),
+                      self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs),
+                      self._w(self.shared_coeffs) if self.shared_coeffs is not None else None, _dptr(self.psi),
                       _dptr(self.workspace), C.c_size_t(self.workspace.numel()), _stream())
         self.steps_done += int(iters)
         return self
