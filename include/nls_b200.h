@@ -164,6 +164,16 @@ int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double 
                     const double *wy, const double *pumping, const double *coeffs,
                     const double *shared_coeffs_host, double *psi,
                     void *workspace, size_t workspace_bytes, nlsb_stream_t stream);
+/* One whole RK4 step of ONE slab of a 2D grid that is decomposed along its slow (row) axis.
+ * psi_in / psi_out / pumping are local arrays of rows_alloc x cols nodes (distinct in/out buffers)
+ * whose row 0 is global row `global_row0` (negative when the slab starts with halo rows above the
+ * domain); local rows [out_row0, out_row1) of psi_out are produced.  Every node read within 4*k rows of
+ * the output rows must hold the current psi (k = (order-1)/2): the caller exchanges those halo rows with
+ * its neighbours between steps.  Rows outside [0, global_rows) are treated as zero.  coeffs_host: 23
+ * coefficients on the HOST.  A node's result does not depend on how the grid is cut into slabs. */
+int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, const double *wx, const double *wy,
+                              int global_row0, int global_rows, int out_row0, int out_row1, const double *pumping,
+                              const double *coeffs_host, const double *psi_in, double *psi_out, nlsb_stream_t stream);
 int nlsb_dev_hamiltonian_2d(int batch, int rows, int cols, int order, const double *wx, const double *wy,
                             const double *pumping, const double *coeffs, const double *u, double *v,
                             nlsb_stream_t stream);

@@ -704,6 +704,26 @@ int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double 
     return 0;
 }
 
+int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, const double *wx, const double *wy,
+                              int global_row0, int global_rows, int out_row0, int out_row1, const double *pumping,
+                              const double *coeffs_host, const double *psi_in, double *psi_out, nlsb_stream_t stream)
+{
+    if (!pumping || !coeffs_host || !psi_in || !psi_out || psi_in == psi_out || rows_alloc < 1 || cols < 1)
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab: bad arguments");
+    if (out_row0 < 0 || out_row1 > rows_alloc || out_row0 > out_row1)
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab: output rows [%d, %d) outside the slab of %d rows", out_row0,
+                    out_row1, rows_alloc);
+    NLSB_TRY(check_order_size(global_rows < cols ? global_rows : cols, order));
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    const RhsCoeffs shared = rhs_coeffs_from(coeffs_host);
+    Fused2DStep s{1, rows_alloc, cols, global_row0, global_rows, out_row0, out_row1,
+                  reinterpret_cast<const double2 *>(psi_in), reinterpret_cast<double2 *>(psi_out), pumping, nullptr, dt,
+                  &shared};
+    NLSB_TRY(launch_rk4_step_fused_2d(order, g_path_2d.load() == 3 ? 1 : 0, s, w, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int nlsb_dev_hamiltonian_2d(int batch, int rows, int cols, int order, const double *wx, const double *wy,
                             const double *pumping, const double *coeffs, const double *u, double *v,
                             nlsb_stream_t stream)

@@ -1,0 +1,263 @@
+"""Multi-GPU execution on one box: ensemble sharding and 2D slab decomposition.
+
+The reference has no parallelism of any kind; these two partitionings are what
+``BASELINE.json`` asks the engine to add:
+
+* **Ensembles** (independent parameter points) shard trivially: rank r advances members
+  ``shard_range(batch, r, world)`` with the single-GPU engine -- no communication on the path.
+* **One large 2D grid** is cut into slabs along its slow (row) axis.  A fused RK4 step consumes a halo
+  of 4k rows (k = (order-1)/2) per side, so neighbours exchange 4k rows ONCE per step (not once per RK
+  stage): point-to-point ``isend/irecv`` to rank +-1 through ``torch.distributed`` (NCCL over NVLink on
+  GPUs, gloo in the CPU tests).  The rows a neighbour needs are computed first on a side stream and
+  sent while the interior rows are still being computed on the main stream.
+
+The arithmetic of a node does not depend on the partition (the kernel treats rows outside the square
+as zero and every node follows the same sequence of roundings), so 1/2/4/8-rank results are bitwise
+identical -- ``tests/test_multigpu_cpu.py`` and ``tests/test_gpu_slabs.py`` check exactly that.
+
+One process per GPU; launch with ``torchrun`` (RANK / LOCAL_RANK / WORLD_SIZE from the environment).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_range", "halo_rows", "SlabPlan", "SlabGrid2D", "advance_emulated"]
+
+STRIP_ROWS = 32   # boundary strips are one tile row of the fused kernel
+
+
+def shard_range(total, rank, world):
+    """Contiguous, balanced range [lo, hi) of `total` items owned by `rank` out of `world`."""
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    return rank * total // world, (rank + 1) * total // world
+
+
+def halo_rows(order):
+    """Rows of psi a fused RK4 step reads beyond the rows it writes: 4 stages x stencil half-width."""
+    if order not in (3, 5, 7):
+        raise ValueError("order must be 3, 5 or 7 (got %r)" % (order,))
+    return 4 * ((order - 1) // 2)
+
+
+class SlabPlan(object):
+    """Row partition of an n-row grid over `world` ranks and the local buffer geometry of one rank."""
+
+    def __init__(self, n, order, rank, world):
+        self.n, self.order, self.rank, self.world = int(n), int(order), int(rank), int(world)
+        self.halo = halo_rows(order)
+        self.row_lo, self.row_hi = shard_range(self.n, rank, world)
+        self.rows_local = self.row_hi - self.row_lo
+        smallest = min(shard_range(self.n, r, world)[1] - shard_range(self.n, r, world)[0] for r in range(world))
+        if world > 1 and smallest < self.halo:
+            raise ValueError("slabs of %d rows are thinner than the %d-row halo: use fewer ranks" % (smallest, self.halo))
+        self.rows_alloc = self.rows_local + 2 * self.halo
+        self.global_row0 = self.row_lo - self.halo            # global row of local row 0
+        self.up = rank - 1 if rank > 0 else None              # neighbour holding the rows above mine
+        self.down = rank + 1 if rank < world - 1 else None
+
+    # local row ranges ---------------------------------------------------------------------------
+    @property
+    def owned(self):
+        return self.halo, self.halo + self.rows_local
+
+    def strips(self):
+        """(top strip, bottom strip, interior) as local row ranges; strips hold the rows neighbours need."""
+        lo, hi = self.owned
+        if self.world == 1:
+            return None, None, (lo, hi)
+        top = (lo, min(lo + STRIP_ROWS, hi))
+        bottom = (max(top[1], hi - STRIP_ROWS), hi)
+        interior = (top[1], bottom[0])
+        return top, (bottom if bottom[1] > bottom[0] else None), (interior if interior[1] > interior[0] else None)
+
+    def send_up(self):       # my first `halo` owned rows -> the lower halo of the rank above
+        lo, _ = self.owned
+        return lo, lo + self.halo
+
+    def send_down(self):     # my last `halo` owned rows -> the upper halo of the rank below
+        _, hi = self.owned
+        return hi - self.halo, hi
+
+    def recv_from_up(self):  # upper halo
+        return 0, self.halo
+
+    def recv_from_down(self):
+        _, hi = self.owned
+        return hi, hi + self.halo
+
+
+def _cuda_stepper(plan, cols, dx, dt, order, coeffs):
+    """The product stepper: one fused RK4 step of a row range through the C ABI."""
+    from . import _lib
+    from .engine import cross_weights
+    wx, wy = cross_weights(order, dx)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+
+    def step(psi_in, psi_out, pumping, row0, row1):
+        _lib.call("nlsb_dev_rk4_step_2d_slab", plan.rows_alloc, cols, order, float(dt),
+                  wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p), plan.global_row0, plan.n,
+                  int(row0), int(row1), C.c_void_p(pumping.data_ptr()), coeffs.ctypes.data_as(C.c_void_p),
+                  C.c_void_p(psi_in.data_ptr()), C.c_void_p(psi_out.data_ptr()),
+                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    step.keepalive = (wx, wy, coeffs)
+    return step
+
+
+class SlabGrid2D(object):
+    """One n x n grid advanced by `world` ranks, each owning a slab of rows (BASELINE config 4).
+
+    pumping, u0: the FULL (n, n) arrays (every rank slices its rows) or a scalar u0.  `stepper` is for
+    the CPU tests only: a callable with the signature of the product stepper above.
+    """
+
+    def __init__(self, n, dx, dt, order=5, pumping=None, coeffs=None, u0=0.1, group=None, device=None, stepper=None,
+                 rank=None, world=None):
+        self.group = group
+        if rank is not None or world is not None:
+            # explicit placement: several slabs emulated inside one process (see advance_emulated)
+            self.rank, self.world = int(rank), int(world)
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.plan = SlabPlan(n, order, self.rank, self.world)
+        self.n, self.dx, self.dt, self.order = int(n), float(dx), float(dt), int(order)
+        self.coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        if self.coeffs.shape != (23,):
+            raise ValueError("coeffs must be a vector of 23 reals")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if stepper is None else torch.device("cpu")
+        self.device = torch.device(device)
+        self.on_gpu = self.device.type == "cuda"
+        p = self.plan
+        self.psi = [torch.zeros((p.rows_alloc, n), dtype=torch.complex128, device=self.device) for _ in range(2)]
+        self.pumping = torch.zeros((p.rows_alloc, n), dtype=torch.float64, device=self.device)
+        self._load(self.pumping, pumping, with_halo=True)
+        self._load(self.psi[0], u0, with_halo=True)
+        self.cur = 0
+        self.steps_done = 0
+        if stepper is None:
+            stepper = _cuda_stepper
+        self.stepper = stepper(p, n, dx, dt, order, self.coeffs)
+        self.side = torch.cuda.Stream(device=self.device) if self.on_gpu else None
+
+    def _load(self, buf, value, with_halo):
+        """Fill a local buffer (owned rows and, from a full array, the halo rows inside the domain)."""
+        p = self.plan
+        g0 = max(p.global_row0, 0) if with_halo else p.row_lo
+        g1 = min(p.global_row0 + p.rows_alloc, p.n) if with_halo else p.row_hi
+        l0 = g0 - p.global_row0
+        if isinstance(value, (int, float, complex)):
+            buf[l0:l0 + (g1 - g0)] = value
+            return
+        arr = value if isinstance(value, torch.Tensor) else torch.from_numpy(np.asarray(value))
+        if tuple(arr.shape) != (p.n, p.n):
+            raise ValueError("expected the full (%d, %d) array, got %r" % (p.n, p.n, tuple(arr.shape)))
+        buf[l0:l0 + (g1 - g0)] = arr[g0:g1].to(device=buf.device, dtype=buf.dtype)
+
+    # ---- halo exchange -------------------------------------------------------------------------------
+    def _exchange(self, buf):
+        p = self.plan
+        ops = []
+        if p.up is not None:
+            a, b = p.send_up()
+            ops.append(dist.P2POp(dist.isend, buf[a:b], p.up, self.group))
+            a, b = p.recv_from_up()
+            ops.append(dist.P2POp(dist.irecv, buf[a:b], p.up, self.group))
+        if p.down is not None:
+            a, b = p.send_down()
+            ops.append(dist.P2POp(dist.isend, buf[a:b], p.down, self.group))
+            a, b = p.recv_from_down()
+            ops.append(dist.P2POp(dist.irecv, buf[a:b], p.down, self.group))
+        if ops:
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+
+    # ---- time stepping -----------------------------------------------------------------------------
+    def advance(self, iters):
+        p = self.plan
+        top, bottom, interior = p.strips()
+        for _ in range(int(iters)):
+            src, dst = self.psi[self.cur], self.psi[1 - self.cur]
+            if self.world == 1:
+                self.stepper(src, dst, self.pumping, *interior)
+            elif self.on_gpu:
+                main = torch.cuda.current_stream(self.device)
+                self.side.wait_stream(main)                       # previous step (and its halos) complete
+                with torch.cuda.stream(self.side):
+                    self.stepper(src, dst, self.pumping, *top)
+                    if bottom:
+                        self.stepper(src, dst, self.pumping, *bottom)
+                    self._exchange(dst)                           # NVLink transfer overlaps the interior below
+                if interior:
+                    self.stepper(src, dst, self.pumping, *interior)
+                main.wait_stream(self.side)
+            else:
+                self.stepper(src, dst, self.pumping, *top)
+                if bottom:
+                    self.stepper(src, dst, self.pumping, *bottom)
+                if interior:
+                    self.stepper(src, dst, self.pumping, *interior)
+                self._exchange(dst)
+            self.cur = 1 - self.cur
+            self.steps_done += 1
+        return self
+
+    def compute_step(self):
+        """One step of this slab WITHOUT the halo exchange (for in-process emulation of several ranks)."""
+        src, dst = self.psi[self.cur], self.psi[1 - self.cur]
+        for rows in self.plan.strips():
+            if rows:
+                self.stepper(src, dst, self.pumping, *rows)
+        return dst
+
+    # ---- results -----------------------------------------------------------------------------------
+    def local_solution(self):
+        lo, hi = self.plan.owned
+        return self.psi[self.cur][lo:hi]
+
+    def gather(self):
+        """The full (n, n) solution as a numpy array on every rank."""
+        local = self.local_solution().contiguous()
+        if self.world == 1:
+            return local.cpu().numpy()
+        most = max(shard_range(self.n, r, self.world)[1] - shard_range(self.n, r, self.world)[0]
+                   for r in range(self.world))
+        padded = torch.zeros((most, self.n), dtype=local.dtype, device=local.device)
+        padded[:local.shape[0]] = local
+        parts = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(parts, padded, group=self.group)
+        rows = []
+        for r, part in enumerate(parts):
+            lo, hi = shard_range(self.n, r, self.world)
+            rows.append(part[:hi - lo].cpu())
+        return torch.cat(rows, dim=0).numpy()
+
+
+def advance_emulated(slabs, iters):
+    """Advance the slabs of ALL ranks inside one process (one GPU or the CPU): every slab computes its
+    step, then halos are copied directly.  Same arithmetic and data movement as the distributed run,
+    used to check partition invariance where only one device is available."""
+    slabs = sorted(slabs, key=lambda g: g.rank)
+    for _ in range(int(iters)):
+        new = [g.compute_step() for g in slabs]
+        for g, buf in zip(slabs, new):
+            p = g.plan
+            if p.up is not None:
+                a, b = p.recv_from_up()
+                c, d = slabs[p.up].plan.send_down()
+                buf[a:b] = new[p.up][c:d]
+            if p.down is not None:
+                a, b = p.recv_from_down()
+                c, d = slabs[p.down].plan.send_up()
+                buf[a:b] = new[p.down][c:d]
+        for g in slabs:
+            g.cur = 1 - g.cur
+            g.steps_done += 1
+    return slabs
