@@ -12,11 +12,30 @@ namespace nlsb {
 //     a   = c3*n - c4 ,  b = c5*|u|^2 + c6*n
 //     v   = (a*u_re + b*u_im - L u_im) + i (a*u_im - b*u_re + L u_re)
 // `cp` is the product c12*P (the reference's own left-to-right association, formed once per solve).
-// The divide is IEEE round-to-nearest, as in the reference.
+// The divide is div_fast below (<= 1 ulp from the reference's correctly rounded divide).
+// a / b without the branchy IEEE slow path: hardware reciprocal seed (MUFU.RCP64H, ~2^-20), two
+// Newton steps, one residual correction of the quotient -- 7 dependent FP64 operations and no control
+// flow, so the scheduler can interleave the chains of the nodes a thread works on.  The result is
+// within 1 ulp of the correctly rounded quotient.  Precondition: b is a finite, normal number (the
+// reservoir denominator c13 + c14 |psi|^2 is >= c13 = 1 for every model the host layer builds); a zero,
+// infinite or NaN denominator yields NaN where IEEE division would yield +-inf / 0.
+__device__ __forceinline__ double div_fast(double a, double b)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+    double e = fma(-b, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-b, x, 1.0);
+    x = fma(x, e, x);
+    const double q = a * x;
+    const double r = fma(-b, q, a);
+    return fma(r, x, q);
+}
+
 __device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, double2 u, double lap_re, double lap_im)
 {
     const double usq = fma(u.x, u.x, u.y * u.y);
-    const double res = cp / fma(c.c14, usq, c.c13);
+    const double res = div_fast(cp, fma(c.c14, usq, c.c13));
     const double a = fma(c.c3, res, -c.c4);
     const double b = fma(c.c5, usq, c.c6 * res);
     double2 v;
