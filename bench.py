@@ -72,7 +72,7 @@ def build_inputs(name, iters=None, batch=None):
         unit = m.getPumping()
         side = int(round(np.sqrt(B)))
         powers = np.linspace(1.0, 40.0, side)
-        gammas = np.geomspace(0.05, 1.0, max(B // side, 1))
+        gammas = np.geomspace(0.05, 1.0, max(-(-B // side), 1))
         P = (powers[:, None, None] * unit[None, None, :]) * np.ones((1, len(gammas), 1))
         C = np.array([dimensionless_coefficients(dict(ORIG, gamma_R=g)) for g in gammas])
         C = np.broadcast_to(C[None], (side, len(gammas), 23))

@@ -22,8 +22,10 @@ namespace {
 
 constexpr int kResidentThreads = 256;   // 255 registers per thread available: taps stay in registers
 
-template <int M, int PPT, bool TAPS_IN_REGS>
-__global__ void __launch_bounds__(kResidentThreads)
+// MINBLOCKS = 2 (<= 128 registers, two CTAs per SM) feeds the FP64 pipe better when an ensemble fills
+// the GPU; a lone system runs faster with all 255 registers (MINBLOCKS = 1, no spills).
+template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS>
+__global__ void __launch_bounds__(kResidentThreads, MINBLOCKS)
 rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, const double *__restrict__ pumping,
                 const double *__restrict__ coeffs, double2 *__restrict__ psi)
 {
@@ -208,7 +210,7 @@ __global__ void band_matvec_1d_kernel(int n, const double *__restrict__ taps, co
     u[i] = fma(sign, s, u[i]);
 }
 
-template <int M, int PPT, bool TAPS_IN_REGS>
+template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS>
 int launch_resident(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
                     const double *coeffs, double2 *psi, cudaStream_t stream)
 {
@@ -216,10 +218,11 @@ int launch_resident(int batch, int n, int iters, double dt, const double *taps, 
     int threads = (n + PPT - 1) / PPT;
     threads = (threads + 31) / 32 * 32;
     const size_t smem = sizeof(double2) * 2 * 2 * K * (threads + 2);
-    cudaError_t e = cudaFuncSetAttribute(rk4_1d_resident<M, PPT, TAPS_IN_REGS>,
+    cudaError_t e = cudaFuncSetAttribute(rk4_1d_resident<M, PPT, TAPS_IN_REGS, MINBLOCKS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    rk4_1d_resident<M, PPT, TAPS_IN_REGS><<<batch, threads, smem, stream>>>(n, iters, dt, taps, pumping, coeffs, psi);
+    rk4_1d_resident<M, PPT, TAPS_IN_REGS, MINBLOCKS><<<batch, threads, smem, stream>>>(n, iters, dt, taps, pumping,
+                                                                                      coeffs, psi);
     count_launches(1);
     return (int)cudaGetLastError();
 }
@@ -228,9 +231,12 @@ template <int M>
 int launch_resident_m(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
                       const double *coeffs, double2 *psi, cudaStream_t stream)
 {
-    if (n <= 4 * kResidentThreads)
-        return launch_resident<M, 4, true>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
-    return launch_resident<M, 8, false>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
+    if (n <= 4 * kResidentThreads) {
+        if (M <= 5 && batch >= 2 * 148)   // enough members for two CTAs on every SM
+            return launch_resident<M, 4, true, (M <= 5) ? 2 : 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
+        return launch_resident<M, 4, true, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
+    }
+    return launch_resident<M, 8, false, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
 }
 
 }  // namespace
