@@ -127,7 +127,8 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
     stage(kStageLast, ya, psi, 0.0);
 }
 
-// 0 = automatic (fused 32x32), 1 = per-stage kernels, 2 = fused 32x32 tiles, 3 = fused 32x64 tiles
+// 0 = automatic (= 4), 1 = per-stage kernels, 2 / 3 = fused 32x32 / 32x64 tiles filled with plain loads from
+// interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy
 static std::atomic<int> g_path_2d{0};
 
 // Coefficients shared by every member of the batch (host copy), or null: set by the entry points that
@@ -203,12 +204,73 @@ int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, do
 int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                           const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream);
 
+// Planar path: psi is split into re/im planes once, every step is one TMA-fed fused launch that
+// ping-pongs between two planar buffers, and the result is interleaved back at the end.
+int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
+                          const double *pumping, const double *coeffs, double2 *psi, double2 *work, int variant,
+                          cudaStream_t stream)
+{
+    Fused2DPlanar p;
+    p.batch = batch; p.rows = rows; p.cols = cols; p.pitch = planar_pitch(cols);
+    p.psi_a = reinterpret_cast<double *>(work);
+    p.psi_b = p.psi_a + planar_psi_doubles(batch, rows, cols);
+    p.cp = p.psi_b + planar_psi_doubles(batch, rows, cols);
+    p.coeffs = coeffs; p.uniform = g_uniform_coeffs; p.dt = dt;
+    PlanarMaps maps;
+    NLSB_TRY(make_planar_maps(order, variant, p, &maps));
+    NLSB_TRY(launch_split_planar(p, psi, pumping, stream));
+
+    auto steps = [&](int first, int count, cudaStream_t s, int *rc) {
+        for (int i = 0; i < count; ++i) {
+            int r = launch_rk4_step_fused_2d_planar(order, variant, p, maps, ((first + i) & 1) == 0, w, s);
+            if (r && !*rc) *rc = r;
+        }
+    };
+    int rc = 0, done = 0;
+    const int chunk = 32;   // even: a replayed chunk starts and ends in buffer A
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NLSB_CUDA(cudaStreamIsCapturing(stream, &cap));
+    if (cap == cudaStreamCaptureStatusNone && iters >= 2 * chunk) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t rec;
+        NLSB_TRY(internal_stream(&rec));
+        NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
+        steps(0, chunk, rec, &rc);
+        cudaError_t e = cudaStreamEndCapture(rec, &graph);
+        count_launches(0ull - (unsigned long long)chunk);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+        for (; done + chunk <= iters; done += chunk) {
+            e = cudaGraphLaunch(exec, stream);
+            if (e != cudaSuccess) break;
+            count_launches((unsigned long long)chunk);
+        }
+        cudaGraphExecDestroy(exec);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+    }
+    steps(done, iters - done, stream, &rc);
+    if (rc) return rc;
+    NLSB_TRY(launch_join_planar(p, (iters & 1) != 0, psi, stream));
+    return 0;
+}
+
 int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                    const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
 {
-    if (g_path_2d.load() == 1)
+    const int path = g_path_2d.load();
+    if (path == 1)
         return enqueue_rk4_2d_staged(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
-    return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
+    if (path == 2 || path == 3 || batch > 32767 || rows > 65535)
+        return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
+    return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, path == 5 ? 1 : 0,
+                                 stream);
 }
 
 int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
@@ -294,7 +356,7 @@ int host_rk4_2d(double dt, const CrossWeights &w, int n, int order, int iters, c
     NLSB_TRY(mem.upload(&d_p, pumping, np));
     NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
     NLSB_TRY(mem.upload(&d_psi, reinterpret_cast<const double2 *>(u0), np));
-    NLSB_TRY(mem.alloc(&d_work, 3 * np));
+    NLSB_TRY(mem.alloc(&d_work, nlsb_dev_rk4_2d_workspace(1, n, n) / sizeof(double2) + 1));
     UniformCoeffsScope uniform(coeffs);
     NLSB_TRY(enqueue_rk4_2d(1, n, n, order, iters, dt, w, d_p, d_c, d_psi, d_work, s));
     NLSB_CUDA(cudaMemcpyAsync(u, d_psi, sizeof(double2) * np, cudaMemcpyDeviceToHost, s));
@@ -379,7 +441,7 @@ unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memo
 
 int nlsb_set_2d_path(int path)
 {
-    if (path < 0 || path > 3) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage), 2 or 3 (fused step)");
+    if (path < 0 || path > 5) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..5 (fused step)");
     g_path_2d.store(path);
     return 0;
 }
@@ -685,7 +747,9 @@ int nlsb_dev_band_matvec_1d(int n, int order, const double *taps, const double *
 size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols)
 {
     if (batch < 1 || rows < 1 || cols < 1) return 0;
-    return sizeof(double2) * 3 * (size_t)batch * rows * cols;
+    const size_t staged = sizeof(double2) * 3 * (size_t)batch * rows * cols;
+    const size_t planar = sizeof(double) * (2 * planar_psi_doubles(batch, rows, cols) + planar_cp_doubles(batch, rows, cols));
+    return (staged > planar ? staged : planar) + 256;
 }
 
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,

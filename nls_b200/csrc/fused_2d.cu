@@ -29,6 +29,10 @@
 #include "device_math.cuh"
 #include "kernels.h"
 
+#include <cuda.h>
+#include <cstdint>
+#include <cstring>
+
 namespace nlsb {
 
 namespace {
@@ -50,8 +54,9 @@ struct FusedCfg {
     static constexpr int NMY = DY / MB_ + TY_ / MB_ + cdiv(3 * K_, MB_);
     static constexpr int H0 = OY + MB_ * NMY + K_;       // frame height
     static constexpr int W1 = 2 * NMX, H1 = MB_ * NMY;   // owned region
-    static constexpr int PLANE0 = W0 * H0, PLANE1 = W1 * H1;
-    static constexpr size_t SMEM = sizeof(double) * (2 * PLANE0 + 5 * PLANE1);
+    // plane sizes rounded up to 128 bytes: every plane is a legal TMA destination
+    static constexpr int PLANE0 = (W0 * H0 + 15) / 16 * 16, PLANE1 = (W1 * H1 + 15) / 16 * 16;
+    static constexpr size_t SMEM = sizeof(double) * (2 * PLANE0 + 5 * PLANE1) + 16;   // + the TMA mbarrier
     static constexpr int TMX0 = (HXL - OX) / 2;          // first tile micro-tile column / row
     static constexpr int TMY0 = DY / MB_;
     static constexpr int TMW = TX / 2, TMH = TY_ / MB_;
@@ -68,9 +73,11 @@ struct FusedArgs {
     int grow0, grows;        // global row index of local row 0, global number of rows
     int out_row0, out_row1;  // local rows [out_row0, out_row1) are written
     int tiles_x, tiles_y;    // tile grid covering cols x (out_row1 - out_row0)
-    const double2 *in;       // [batch][rows][cols]
+    const double2 *in;       // [batch][rows][cols]   (interleaved kernels)
     double2 *out;            // [batch][rows][cols]
     const double *pumping;   // [batch][rows][cols]
+    double *pout;            // planar kernels: output planes [batch][2][rows][pitch]
+    int pitch;
     const double *coeffs;    // [batch][23] (per-member coefficients) -- unused when UNIFORM
     RhsCoeffs cu;            // coefficients shared by every member (UNIFORM kernels read them from the
                              // constant bank instead of pinning 14 registers)
@@ -137,6 +144,13 @@ struct TileCtx {
     double half_dt, dt, dt6;
 };
 
+// Where the new psi goes: interleaved complex (aos) or separate planes (planar working copy).
+struct OutRef {
+    double2 *aos;
+    double *re, *im;
+    int pitch;
+};
+
 // Per-thread state of the tile micro-tile a thread owns for the whole step.
 template <int MB>
 struct Owned {
@@ -147,10 +161,10 @@ struct Owned {
 
 // One micro-tile of stage S.  OWNED: the thread's own tile micro-tile (state in registers,
 // writes the new psi in stage 4); otherwise a stateless ring micro-tile.
-template <typename C, int S, bool OWNED>
+template <typename C, int S, bool OWNED, bool PLANAR>
 __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, const RhsCoeffs &c,
                                            const double (&wx)[2 * C::K + 1], const double (&wy)[2 * C::K + 1],
-                                           int mx, int my, Owned<C::MB> &own, double2 *__restrict__ out)
+                                           int mx, int my, Owned<C::MB> &own, const OutRef &out)
 {
     constexpr int K = C::K, PH = C::PH, MB = C::MB;
     // stage input: S=1 psi frame; S=2 frame 1; S=3 frame 2; S=4 frame 1.  Output: 1, 2, 1.
@@ -289,27 +303,38 @@ __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, 
             }
         } else if (OWNED) {
             if (rowin && ly >= t.out_row0 && ly < t.out_row1) {
-                double2 *q = out + (size_t)ly * t.cols + gx;
-                if (colin0) q[0] = make_double2(yr[0], yi[0]);
-                if (colin1) q[1] = make_double2(yr[1], yi[1]);
+                if (PLANAR) {
+                    const size_t o = (size_t)ly * out.pitch + gx;      // even: 16-byte aligned pair
+                    if (colin1) {
+                        *reinterpret_cast<double2 *>(out.re + o) = make_double2(yr[0], yr[1]);
+                        *reinterpret_cast<double2 *>(out.im + o) = make_double2(yi[0], yi[1]);
+                    } else if (colin0) {
+                        out.re[o] = yr[0];
+                        out.im[o] = yi[0];
+                    }
+                } else {
+                    double2 *q = out.aos + (size_t)ly * t.cols + gx;
+                    if (colin0) q[0] = make_double2(yr[0], yi[0]);
+                    if (colin1) q[1] = make_double2(yr[1], yi[1]);
+                }
             }
         }
     }
 }
 
-template <typename C, int S>
+template <typename C, int S, bool PLANAR>
 __device__ __forceinline__ void run_stage(const Smem<C> &sm, const TileCtx &t, const RhsCoeffs &c,
                                           const double (&wx)[2 * C::K + 1], const double (&wy)[2 * C::K + 1],
-                                          Owned<C::MB> &own, double2 *__restrict__ out)
+                                          Owned<C::MB> &own, const OutRef &out)
 {
     using G = StageGrid<C, S>;
     const int tid = threadIdx.x;
-    micro_tile<C, S, true>(sm, t, c, wx, wy, C::TMX0 + tid % C::TMW, C::TMY0 + tid / C::TMW, own, out);
+    micro_tile<C, S, true, PLANAR>(sm, t, c, wx, wy, C::TMX0 + tid % C::TMW, C::TMY0 + tid / C::TMW, own, out);
     if (S < 4) {
         for (int idx = tid; idx < G::NRING; idx += C::THREADS) {
             int mx, my;
             G::locate(idx, mx, my);
-            micro_tile<C, S, false>(sm, t, c, wx, wy, mx, my, own, out);
+            micro_tile<C, S, false, PLANAR>(sm, t, c, wx, wy, mx, my, own, out);
         }
     }
 }
@@ -320,12 +345,46 @@ struct WeightsArg {
     double wy[2 * K + 1];
 };
 
-template <typename C, bool UNIFORM>
+// ---- TMA / mbarrier primitives (PTX as emitted by CUTLASS's SM90_TMA_LOAD_3D and ClusterTransactionBarrier) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *map, uint32_t bar, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+struct TensorMap {
+    alignas(64) unsigned char bytes[128];
+};
+
+template <typename C, bool UNIFORM, bool TMA>
 __global__ void __launch_bounds__(C::THREADS, C::MINBLOCKS)
-rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ WeightsArg<C::K> wa)
+rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ WeightsArg<C::K> wa,
+                      const __grid_constant__ TensorMap map_in, const __grid_constant__ TensorMap map_cp)
 {
     constexpr int K = C::K;
-    extern __shared__ __align__(16) double smem_raw[];
+    extern __shared__ __align__(128) double smem_raw[];
     Smem<C> sm{smem_raw};
 
     const int tid = threadIdx.x;
@@ -333,8 +392,19 @@ rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant
     const size_t member = blockIdx.y;
     const size_t plane = (size_t)a.rows * a.cols;
     const double2 *__restrict__ in = a.in + member * plane;
-    double2 *__restrict__ out = a.out + member * plane;
     const double *__restrict__ P = a.pumping + member * plane;
+    OutRef out;
+    if (TMA) {
+        const size_t pplane = (size_t)a.rows * a.pitch;
+        out.aos = nullptr;
+        out.re = a.pout + (2 * member) * pplane;
+        out.im = a.pout + (2 * member + 1) * pplane;
+        out.pitch = a.pitch;
+    } else {
+        out.aos = a.out + member * plane;
+        out.re = out.im = nullptr;
+        out.pitch = 0;
+    }
     const RhsCoeffs c = UNIFORM ? a.cu : load_rhs_coeffs(a.coeffs + member * 23);
 
     TileCtx t;
@@ -348,6 +418,21 @@ rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 2 * K + 1; ++i) { wx[i] = wa.wx[i]; wy[i] = wa.wy[i]; }
 
+    if (TMA) {
+        // ---- fill by TMA: three boxes (re frame, im frame, c12*P); elements outside the arrays arrive
+        // as zeros, which is exactly the truncated (zero outside the square) stencil boundary ----
+        const uint32_t bar = smem_u32(smem_raw + 2 * C::PLANE0 + 5 * C::PLANE1);
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            constexpr uint32_t bytes = sizeof(double) * (2 * C::W0 * C::H0 + C::W1 * C::H1);
+            mbar_expect_tx(bar, bytes);
+            tma_load_3d(smem_u32(sm.re0()), &map_in, bar, t.x0, t.y0, (int)(2 * member));
+            tma_load_3d(smem_u32(sm.im0()), &map_in, bar, t.x0, t.y0, (int)(2 * member + 1));
+            tma_load_3d(smem_u32(sm.cp()), &map_cp, bar, t.x0 + C::OX, t.y0 + C::OY, (int)member);
+        }
+        mbar_wait(bar, 0);
+    } else {
     // ---- fill: psi frame (zero outside the local array / the domain), loads batched 4 deep -------
     {
         double *b0r = sm.re0(), *b0i = sm.im0();
@@ -406,34 +491,51 @@ rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant
         }
     }
     __syncthreads();
+    }
 
     Owned<C::MB> own;
-    run_stage<C, 1>(sm, t, c, wx, wy, own, out);
+    run_stage<C, 1, TMA>(sm, t, c, wx, wy, own, out);
     __syncthreads();
-    run_stage<C, 2>(sm, t, c, wx, wy, own, out);
+    run_stage<C, 2, TMA>(sm, t, c, wx, wy, own, out);
     __syncthreads();
-    run_stage<C, 3>(sm, t, c, wx, wy, own, out);
+    run_stage<C, 3, TMA>(sm, t, c, wx, wy, own, out);
     __syncthreads();
-    run_stage<C, 4>(sm, t, c, wx, wy, own, out);
+    run_stage<C, 4, TMA>(sm, t, c, wx, wy, own, out);
 }
 
-template <typename C, bool UNIFORM>
-int launch_fused_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+template <typename C, bool UNIFORM, bool TMA>
+int configure_fused()
 {
-    constexpr int K = C::K;
     static bool configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(rk4_step_fused_kernel<C, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(rk4_step_fused_kernel<C, UNIFORM, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(rk4_step_fused_kernel<C, UNIFORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(rk4_step_fused_kernel<C, UNIFORM, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
     }
-    FusedArgs a;
+    return 0;
+}
+
+template <typename C>
+WeightsArg<C::K> pack_weights(const CrossWeights &w)
+{
+    WeightsArg<C::K> wa;
+    for (int i = 0; i < 2 * C::K + 1; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
+    return wa;
+}
+
+template <typename C, bool UNIFORM>
+int launch_fused_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    int rc = configure_fused<C, UNIFORM, false>();
+    if (rc) return rc;
+    FusedArgs a{};
     a.rows = s.rows; a.cols = s.cols; a.grow0 = s.grow0; a.grows = s.grows;
     a.out_row0 = s.out_row0; a.out_row1 = s.out_row1;
     a.tiles_x = (s.cols + C::TX - 1) / C::TX;
@@ -442,10 +544,34 @@ int launch_fused_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t s
     if (UNIFORM) a.cu = *s.uniform;
     a.dt = s.dt; a.half_dt = s.dt / 2; a.dt6 = s.dt / 6;
     if (a.tiles_x <= 0 || a.tiles_y <= 0) return 0;
-    WeightsArg<K> wa;
-    for (int i = 0; i < 2 * K + 1; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
     const dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)s.batch);
-    rk4_step_fused_kernel<C, UNIFORM><<<grid, C::THREADS, C::SMEM, stream>>>(a, wa);
+    TensorMap none{};
+    rk4_step_fused_kernel<C, UNIFORM, false><<<grid, C::THREADS, C::SMEM, stream>>>(a, pack_weights<C>(w), none, none);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+template <typename C, bool UNIFORM>
+int launch_fused_planar_cfg(const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b, const CrossWeights &w,
+                            cudaStream_t stream)
+{
+    int rc = configure_fused<C, UNIFORM, true>();
+    if (rc) return rc;
+    FusedArgs a{};
+    a.rows = p.rows; a.cols = p.cols; a.grow0 = 0; a.grows = p.rows;
+    a.out_row0 = 0; a.out_row1 = p.rows;
+    a.tiles_x = (p.cols + C::TX - 1) / C::TX;
+    a.tiles_y = (p.rows + C::TY - 1) / C::TY;
+    a.pout = a_to_b ? p.psi_b : p.psi_a;
+    a.pitch = p.pitch;
+    a.coeffs = p.coeffs;
+    if (UNIFORM) a.cu = *p.uniform;
+    a.dt = p.dt; a.half_dt = p.dt / 2; a.dt6 = p.dt / 6;
+    TensorMap in, cp;
+    std::memcpy(in.bytes, a_to_b ? maps.psi_a : maps.psi_b, 128);
+    std::memcpy(cp.bytes, maps.cp, 128);
+    const dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)p.batch);
+    rk4_step_fused_kernel<C, UNIFORM, true><<<grid, C::THREADS, C::SMEM, stream>>>(a, pack_weights<C>(w), in, cp);
     count_launches(1);
     return (int)cudaGetLastError();
 }
@@ -454,16 +580,139 @@ int launch_fused_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t s
 // hide behind the other's arithmetic); variant 1: 32x64 tiles, 512 threads, one CTA per SM (less
 // redundant halo work).
 template <int K>
-int launch_fused_k(int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
-{
+struct Shapes {
     using Small = FusedCfg<K, 32, 2, 256, (K == 3) ? 1 : 2>;
     using Tall = FusedCfg<(K == 3) ? 2 : K, 64, 2, 512, 1>;
+};
+
+template <int K>
+int launch_fused_k(int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    using Small = typename Shapes<K>::Small;
+    using Tall = typename Shapes<K>::Tall;
     if (K == 3 || variant == 0)
         return s.uniform ? launch_fused_cfg<Small, true>(s, w, stream) : launch_fused_cfg<Small, false>(s, w, stream);
     return s.uniform ? launch_fused_cfg<Tall, true>(s, w, stream) : launch_fused_cfg<Tall, false>(s, w, stream);
 }
 
+template <int K>
+int launch_fused_planar_k(int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
+                          const CrossWeights &w, cudaStream_t stream)
+{
+    using Small = typename Shapes<K>::Small;
+    using Tall = typename Shapes<K>::Tall;
+    if (K == 3 || variant == 0)
+        return p.uniform ? launch_fused_planar_cfg<Small, true>(p, maps, a_to_b, w, stream)
+                         : launch_fused_planar_cfg<Small, false>(p, maps, a_to_b, w, stream);
+    return p.uniform ? launch_fused_planar_cfg<Tall, true>(p, maps, a_to_b, w, stream)
+                     : launch_fused_planar_cfg<Tall, false>(p, maps, a_to_b, w, stream);
+}
+
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_plane_map(void *out128, double *base, int cols, int rows, int planes, int pitch, int box_w, int box_h)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(NLSB_EINVAL, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(double), (cuuint64_t)pitch * rows * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSB_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    std::memcpy(out128, &map, 128);
+    return 0;
+}
+
+template <typename C>
+int make_maps_cfg(const Fused2DPlanar &p, PlanarMaps *maps)
+{
+    int rc = encode_plane_map(maps->psi_a, p.psi_a, p.cols, p.rows, 2 * p.batch, p.pitch, C::W0, C::H0);
+    if (!rc) rc = encode_plane_map(maps->psi_b, p.psi_b, p.cols, p.rows, 2 * p.batch, p.pitch, C::W0, C::H0);
+    if (!rc) rc = encode_plane_map(maps->cp, p.cp, p.cols, p.rows, p.batch, p.pitch, C::W1, C::H1);
+    return rc;
+}
+
+template <int K>
+int make_maps_k(int variant, const Fused2DPlanar &p, PlanarMaps *maps)
+{
+    if (K == 3 || variant == 0) return make_maps_cfg<typename Shapes<K>::Small>(p, maps);
+    return make_maps_cfg<typename Shapes<K>::Tall>(p, maps);
+}
+
+// ---- interleaved <-> planar ---------------------------------------------------------------------
+__global__ void split_planar_kernel(int rows, int cols, int pitch, const double2 *__restrict__ psi,
+                                    const double *__restrict__ pumping, const double *__restrict__ coeffs,
+                                    double *__restrict__ planes, double *__restrict__ cp)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const size_t member = blockIdx.z;
+    if (x >= pitch) return;
+    const size_t pplane = (size_t)rows * pitch, o = (size_t)y * pitch + x;
+    double2 v = make_double2(0.0, 0.0);
+    double c = 0.0;
+    if (x < cols) {
+        const size_t g = (member * rows + y) * cols + x;
+        v = psi[g];
+        c = coeffs[member * 23 + 11] * pumping[g];     // c12 * P, rounded once (nls.f90:580 association)
+    }
+    planes[(2 * member) * pplane + o] = v.x;
+    planes[(2 * member + 1) * pplane + o] = v.y;
+    cp[member * pplane + o] = c;
+}
+
+__global__ void join_planar_kernel(int rows, int cols, int pitch, const double *__restrict__ planes,
+                                   double2 *__restrict__ psi)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const size_t member = blockIdx.z;
+    if (x >= cols) return;
+    const size_t pplane = (size_t)rows * pitch, o = (size_t)y * pitch + x;
+    psi[(member * rows + y) * cols + x] = make_double2(planes[(2 * member) * pplane + o], planes[(2 * member + 1) * pplane + o]);
+}
+
 }  // namespace
+
+int make_planar_maps(int order, int variant, const Fused2DPlanar &p, PlanarMaps *maps)
+{
+    switch (order) {
+    case 3: return make_maps_k<1>(variant, p, maps);
+    case 5: return make_maps_k<2>(variant, p, maps);
+    case 7: return make_maps_k<3>(variant, p, maps);
+    }
+    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
+
+int launch_split_planar(const Fused2DPlanar &p, const double2 *psi, const double *pumping, cudaStream_t stream)
+{
+    if (p.rows > 65535 || p.batch > 65535) return fail(NLSB_ESIZE, "planar split: rows/batch exceed the grid limits");
+    const dim3 block(128), grid((p.pitch + 127) / 128, p.rows, p.batch);
+    split_planar_kernel<<<grid, block, 0, stream>>>(p.rows, p.cols, p.pitch, psi, pumping, p.coeffs, p.psi_a, p.cp);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int launch_join_planar(const Fused2DPlanar &p, bool from_b, double2 *psi, cudaStream_t stream)
+{
+    const dim3 block(128), grid((p.cols + 127) / 128, p.rows, p.batch);
+    join_planar_kernel<<<grid, block, 0, stream>>>(p.rows, p.cols, p.pitch, from_b ? p.psi_b : p.psi_a, psi);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
 
 int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
 {
@@ -472,6 +721,18 @@ int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const
     case 3: return launch_fused_k<1>(variant, s, w, stream);
     case 5: return launch_fused_k<2>(variant, s, w, stream);
     case 7: return launch_fused_k<3>(variant, s, w, stream);
+    }
+    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
+
+int launch_rk4_step_fused_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
+                                    const CrossWeights &w, cudaStream_t stream)
+{
+    if (p.batch > 32767) return fail(NLSB_ESIZE, "batch = %d exceeds the planar-path limit 32767", p.batch);
+    switch (order) {
+    case 3: return launch_fused_planar_k<1>(variant, p, maps, a_to_b, w, stream);
+    case 5: return launch_fused_planar_k<2>(variant, p, maps, a_to_b, w, stream);
+    case 7: return launch_fused_planar_k<3>(variant, p, maps, a_to_b, w, stream);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
 }

@@ -52,6 +52,32 @@ struct Fused2DStep {
 };
 // variant 0: 32x32 tiles, two CTAs per SM; variant 1: 32x64 tiles, one CTA of 512 threads per SM
 int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
+// Planar (re-plane / im-plane) working copy of psi used by the whole-grid time loop: lets the fused
+// kernel fetch its frames with TMA (cp.async.bulk.tensor, out-of-bounds zero fill = the truncated
+// stencil boundary).  Layout: psi planes [batch][2][rows][pitch], c12*P [batch][rows][pitch], pitch even.
+struct PlanarMaps {
+    alignas(64) unsigned char psi_a[128];   // CUtensorMap of buffer A, buffer B, and of c12*P
+    alignas(64) unsigned char psi_b[128];
+    alignas(64) unsigned char cp[128];
+};
+struct Fused2DPlanar {
+    int batch, rows, cols, pitch;
+    double *psi_a, *psi_b;   // two planar psi buffers (ping-pong)
+    double *cp;              // c12 * P
+    const double *coeffs;    // [batch][23] on the device
+    const RhsCoeffs *uniform;
+    double dt;
+};
+inline int planar_pitch(int cols) { return (cols + 1) & ~1; }
+inline size_t planar_psi_doubles(int batch, int rows, int cols) { return (size_t)2 * batch * rows * planar_pitch(cols); }
+inline size_t planar_cp_doubles(int batch, int rows, int cols) { return (size_t)batch * rows * planar_pitch(cols); }
+int make_planar_maps(int order, int variant, const Fused2DPlanar &p, PlanarMaps *maps);
+// psi (interleaved) -> planes of buffer A, and c12*P; buffer A/B -> psi (interleaved)
+int launch_split_planar(const Fused2DPlanar &p, const double2 *psi, const double *pumping, cudaStream_t stream);
+int launch_join_planar(const Fused2DPlanar &p, bool from_b, double2 *psi, cudaStream_t stream);
+// one RK4 step A -> B (a_to_b) or B -> A
+int launch_rk4_step_fused_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
+                                    const CrossWeights &w, cudaStream_t stream);
 int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
                            double sign, cudaStream_t stream);
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,
