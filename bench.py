@@ -239,7 +239,7 @@ def run_engine(args):
     if slabs:
         from nls_b200.multigpu import SlabGrid2D
         eng = SlabGrid2D(w["n"], w["dx"], w["dt"], w["order"], w["pumping"][0], w["coeffs"][0], w["u0"][0], device=dev)
-        psi0 = eng.psi[eng.cur].clone()
+        psi0 = eng.state_buffer().clone()
     elif w["dim"] == 1:
         eng = Ensemble1D(w["n"], w["dx"], w["dt"], order=w["order"], batch=w["batch"], pumping=w["pumping"],
                          coeffs=w["coeffs"], u0=w["u0"], device=dev)
@@ -250,7 +250,7 @@ def run_engine(args):
         psi0 = eng.psi.clone()
 
     def reset():
-        (eng.psi[eng.cur] if slabs else eng.psi).copy_(psi0)
+        eng.set_local_state(psi0) if slabs else eng.psi.copy_(psi0)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -282,7 +282,7 @@ def run_engine(args):
         t_wall = time.perf_counter() - t_wall0
     launches = _lib.kernel_launches() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in events)
-    final = (eng.psi[eng.cur] if slabs else eng.psi).clone()
+    final = (eng.state_buffer() if slabs else eng.psi).clone()
 
     # end to end: host buffers through the reference-facing entry point (H2D + solve + D2H per step)
     e2e = None

@@ -176,6 +176,17 @@ int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double 
 int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, const double *wx, const double *wy,
                               int global_row0, int global_rows, int out_row0, int out_row1, const double *pumping,
                               const double *coeffs_host, const double *psi_in, double *psi_out, nlsb_stream_t stream);
+/* The same slab step on the PLANAR layout the TMA-fed kernel reads: planes_in / planes_out hold the
+ * real plane then the imaginary plane, each rows_alloc x pitch doubles with pitch = nlsb_planar_pitch(cols)
+ * (cols rounded up to even, so rows are 16-byte aligned); cp is c12*P in the same rows_alloc x pitch
+ * layout.  Padding columns and rows outside the square must be zero in planes_in (the kernel never
+ * writes them).  Tiles are fetched with cp.async.bulk.tensor; elements outside the local arrays arrive
+ * as zeros. */
+int nlsb_planar_pitch(int cols);
+int nlsb_dev_rk4_step_2d_slab_planar(int rows_alloc, int cols, int order, double dt, const double *wx,
+                                     const double *wy, int global_row0, int global_rows, int out_row0, int out_row1,
+                                     const double *cp, const double *coeffs_host, double *planes_in, double *planes_out,
+                                     nlsb_stream_t stream);
 int nlsb_dev_hamiltonian_2d(int batch, int rows, int cols, int order, const double *wx, const double *wy,
                             const double *pumping, const double *coeffs, const double *u, double *v,
                             nlsb_stream_t stream);

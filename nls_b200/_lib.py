@@ -61,6 +61,8 @@ PROTOTYPES = {
     "nlsb_set_2d_path": (_I, [_I]),
     "nlsb_dev_rk4_2d": (_I, [_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "nlsb_dev_rk4_step_2d_slab": (_I, [_I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "nlsb_planar_pitch": (_I, [_I]),
+    "nlsb_dev_rk4_step_2d_slab_planar": (_I, [_I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "nlsb_dev_hamiltonian_2d": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "nlsb_dev_cross_matvec_2d": (_I, [_I, _I, _I, _P, _P, _P, _P, _F, _P]),
     "nlsb_dev_reservoir": (_I, [_Z, _P, _P, _P, _P, _P]),

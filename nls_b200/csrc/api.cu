@@ -212,6 +212,7 @@ int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, d
 {
     Fused2DPlanar p;
     p.batch = batch; p.rows = rows; p.cols = cols; p.pitch = planar_pitch(cols);
+    p.grow0 = 0; p.grows = rows; p.out_row0 = 0; p.out_row1 = rows;
     p.psi_a = reinterpret_cast<double *>(work);
     p.psi_b = p.psi_a + planar_psi_doubles(batch, rows, cols);
     p.cp = p.psi_b + planar_psi_doubles(batch, rows, cols);
@@ -785,6 +786,34 @@ int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, co
                   reinterpret_cast<const double2 *>(psi_in), reinterpret_cast<double2 *>(psi_out), pumping, nullptr, dt,
                   &shared};
     NLSB_TRY(launch_rk4_step_fused_2d(order, g_path_2d.load() == 3 ? 1 : 0, s, w, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_planar_pitch(int cols) { return cols > 0 ? planar_pitch(cols) : 0; }
+
+int nlsb_dev_rk4_step_2d_slab_planar(int rows_alloc, int cols, int order, double dt, const double *wx,
+                                     const double *wy, int global_row0, int global_rows, int out_row0, int out_row1,
+                                     const double *cp, const double *coeffs_host, double *planes_in, double *planes_out,
+                                     nlsb_stream_t stream)
+{
+    if (!cp || !coeffs_host || !planes_in || !planes_out || planes_in == planes_out || rows_alloc < 1 || cols < 1)
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_planar: bad arguments");
+    if (out_row0 < 0 || out_row1 > rows_alloc || out_row0 > out_row1)
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_planar: output rows [%d, %d) outside the slab of %d rows",
+                    out_row0, out_row1, rows_alloc);
+    NLSB_TRY(check_order_size(global_rows < cols ? global_rows : cols, order));
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    const RhsCoeffs shared = rhs_coeffs_from(coeffs_host);
+    const int variant = g_path_2d.load() == 5 ? 1 : 0;
+    Fused2DPlanar p;
+    p.batch = 1; p.rows = rows_alloc; p.cols = cols; p.pitch = planar_pitch(cols);
+    p.grow0 = global_row0; p.grows = global_rows; p.out_row0 = out_row0; p.out_row1 = out_row1;
+    p.psi_a = planes_in; p.psi_b = planes_out; p.cp = const_cast<double *>(cp);
+    p.coeffs = nullptr; p.uniform = &shared; p.dt = dt;
+    PlanarMaps maps;
+    NLSB_TRY(make_planar_maps(order, variant, p, &maps));
+    NLSB_TRY(launch_rk4_step_fused_2d_planar(order, variant, p, maps, true, w, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -558,10 +558,11 @@ int launch_fused_planar_cfg(const Fused2DPlanar &p, const PlanarMaps &maps, bool
     int rc = configure_fused<C, UNIFORM, true>();
     if (rc) return rc;
     FusedArgs a{};
-    a.rows = p.rows; a.cols = p.cols; a.grow0 = 0; a.grows = p.rows;
-    a.out_row0 = 0; a.out_row1 = p.rows;
+    a.rows = p.rows; a.cols = p.cols; a.grow0 = p.grow0; a.grows = p.grows;
+    a.out_row0 = p.out_row0; a.out_row1 = p.out_row1;
     a.tiles_x = (p.cols + C::TX - 1) / C::TX;
-    a.tiles_y = (p.rows + C::TY - 1) / C::TY;
+    a.tiles_y = (p.out_row1 - p.out_row0 + C::TY - 1) / C::TY;
+    if (a.tiles_x <= 0 || a.tiles_y <= 0) return 0;
     a.pout = a_to_b ? p.psi_b : p.psi_a;
     a.pitch = p.pitch;
     a.coeffs = p.coeffs;

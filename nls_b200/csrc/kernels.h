@@ -62,6 +62,8 @@ struct PlanarMaps {
 };
 struct Fused2DPlanar {
     int batch, rows, cols, pitch;
+    int grow0, grows;        // slab decomposition: global row of local row 0, global row count (else 0, rows)
+    int out_row0, out_row1;  // local rows to produce (else 0, rows)
     double *psi_a, *psi_b;   // two planar psi buffers (ping-pong)
     double *cp;              // c12 * P
     const double *coeffs;    // [batch][23] on the device

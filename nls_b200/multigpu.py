@@ -93,20 +93,22 @@ class SlabPlan(object):
 
 
 def _cuda_stepper(plan, cols, dx, dt, order, coeffs):
-    """The product stepper: one fused RK4 step of a row range through the C ABI."""
+    """The product stepper: one fused RK4 step of a row range through the C ABI, on the planar layout
+    (re plane, im plane, c12*P) that the kernel fetches with TMA."""
     from . import _lib
     from .engine import cross_weights
     wx, wy = cross_weights(order, dx)
     coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
 
-    def step(psi_in, psi_out, pumping, row0, row1):
-        _lib.call("nlsb_dev_rk4_step_2d_slab", plan.rows_alloc, cols, order, float(dt),
+    def step(planes_in, planes_out, cp, row0, row1):
+        _lib.call("nlsb_dev_rk4_step_2d_slab_planar", plan.rows_alloc, cols, order, float(dt),
                   wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p), plan.global_row0, plan.n,
-                  int(row0), int(row1), C.c_void_p(pumping.data_ptr()), coeffs.ctypes.data_as(C.c_void_p),
-                  C.c_void_p(psi_in.data_ptr()), C.c_void_p(psi_out.data_ptr()),
+                  int(row0), int(row1), C.c_void_p(cp.data_ptr()), coeffs.ctypes.data_as(C.c_void_p),
+                  C.c_void_p(planes_in.data_ptr()), C.c_void_p(planes_out.data_ptr()),
                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
     step.keepalive = (wx, wy, coeffs)
+    step.planar = True
     return step
 
 
@@ -136,15 +138,30 @@ class SlabGrid2D(object):
         self.device = torch.device(device)
         self.on_gpu = self.device.type == "cuda"
         p = self.plan
-        self.psi = [torch.zeros((p.rows_alloc, n), dtype=torch.complex128, device=self.device) for _ in range(2)]
-        self.pumping = torch.zeros((p.rows_alloc, n), dtype=torch.float64, device=self.device)
-        self._load(self.pumping, pumping, with_halo=True)
-        self._load(self.psi[0], u0, with_halo=True)
-        self.cur = 0
-        self.steps_done = 0
         if stepper is None:
             stepper = _cuda_stepper
         self.stepper = stepper(p, n, dx, dt, order, self.coeffs)
+        self.planar = bool(getattr(self.stepper, "planar", False))
+        pumping_buf = torch.zeros((p.rows_alloc, n), dtype=torch.float64, device=self.device)
+        psi0 = torch.zeros((p.rows_alloc, n), dtype=torch.complex128, device=self.device)
+        self._load(pumping_buf, pumping, with_halo=True)
+        self._load(psi0, u0, with_halo=True)
+        if self.planar:
+            # re plane, im plane and c12*P, rows padded to an even pitch (16-byte aligned rows for TMA);
+            # padding columns and rows outside the square are zero and are never written
+            from . import _lib
+            self.pitch = int(_lib.load().nlsb_planar_pitch(n))
+            self.psi = [torch.zeros((2, p.rows_alloc, self.pitch), dtype=torch.float64, device=self.device)
+                        for _ in range(2)]
+            self.psi[0][0, :, :n] = psi0.real
+            self.psi[0][1, :, :n] = psi0.imag
+            self.pumping = torch.zeros((p.rows_alloc, self.pitch), dtype=torch.float64, device=self.device)
+            self.pumping[:, :n] = float(self.coeffs[11]) * pumping_buf      # c12 * P (nls.f90:580 association)
+        else:
+            self.psi = [psi0, torch.zeros_like(psi0)]
+            self.pumping = pumping_buf
+        self.cur = 0
+        self.steps_done = 0
         self.side = torch.cuda.Stream(device=self.device) if self.on_gpu else None
 
     def _load(self, buf, value, with_halo):
@@ -165,16 +182,18 @@ class SlabGrid2D(object):
     def _exchange(self, buf):
         p = self.plan
         ops = []
-        if p.up is not None:
-            a, b = p.send_up()
-            ops.append(dist.P2POp(dist.isend, buf[a:b], p.up, self.group))
-            a, b = p.recv_from_up()
-            ops.append(dist.P2POp(dist.irecv, buf[a:b], p.up, self.group))
-        if p.down is not None:
-            a, b = p.send_down()
-            ops.append(dist.P2POp(dist.isend, buf[a:b], p.down, self.group))
-            a, b = p.recv_from_down()
-            ops.append(dist.P2POp(dist.irecv, buf[a:b], p.down, self.group))
+        parts = [buf[0], buf[1]] if self.planar else [buf]     # planar: the rows of both planes travel
+        for part in parts:
+            if p.up is not None:
+                a, b = p.send_up()
+                ops.append(dist.P2POp(dist.isend, part[a:b], p.up, self.group))
+                a, b = p.recv_from_up()
+                ops.append(dist.P2POp(dist.irecv, part[a:b], p.up, self.group))
+            if p.down is not None:
+                a, b = p.send_down()
+                ops.append(dist.P2POp(dist.isend, part[a:b], p.down, self.group))
+                a, b = p.recv_from_down()
+                ops.append(dist.P2POp(dist.irecv, part[a:b], p.down, self.group))
         if ops:
             for work in dist.batch_isend_irecv(ops):
                 work.wait()
@@ -220,7 +239,17 @@ class SlabGrid2D(object):
     # ---- results -----------------------------------------------------------------------------------
     def local_solution(self):
         lo, hi = self.plan.owned
-        return self.psi[self.cur][lo:hi]
+        buf = self.psi[self.cur]
+        if self.planar:
+            return torch.complex(buf[0, lo:hi, :self.n], buf[1, lo:hi, :self.n])
+        return buf[lo:hi]
+
+    def set_local_state(self, other_buffer):
+        """Overwrite the current state buffer (same layout) -- used by bench.py to reset between runs."""
+        self.psi[self.cur].copy_(other_buffer)
+
+    def state_buffer(self):
+        return self.psi[self.cur]
 
     def gather(self):
         """The full (n, n) solution as a numpy array on every rank."""
@@ -252,11 +281,11 @@ def advance_emulated(slabs, iters):
             if p.up is not None:
                 a, b = p.recv_from_up()
                 c, d = slabs[p.up].plan.send_down()
-                buf[a:b] = new[p.up][c:d]
+                buf[..., a:b, :] = new[p.up][..., c:d, :]
             if p.down is not None:
                 a, b = p.recv_from_down()
                 c, d = slabs[p.down].plan.send_up()
-                buf[a:b] = new[p.down][c:d]
+                buf[..., a:b, :] = new[p.down][..., c:d, :]
         for g in slabs:
             g.cur = 1 - g.cur
             g.steps_done += 1
