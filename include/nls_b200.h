@@ -159,8 +159,10 @@ int nlsb_dev_band_matvec_1d(int n, int order, const double *taps, const double *
 size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols);
 /* Which kernels advance 2D grids: 0 = automatic (fused whole-step kernel, 32x32 tiles, TMA fill from a
  * planar working copy), 1 = one launch per RK stage, 2 / 3 = fused with 32x32 / 32x64 tiles filled by
- * plain loads, 4 / 5 = fused with 32x32 / 32x64 tiles filled by TMA.  All give the same result to
- * rounding (the fused variants bitwise); the switch exists for tests and profiling. */
+ * plain loads, 4 / 5 = fused with 32x32 / 32x64 tiles filled by TMA, 6 / 7 = as 4 / 5 but the whole time
+ * loop in one persistent launch when every tile is resident at once (experimental, slower).  All
+ * give the same result to rounding (the fused variants bitwise); the switch exists for tests and
+ * profiling. */
 int nlsb_set_2d_path(int path);
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
                     const double *wy, const double *pumping, const double *coeffs,

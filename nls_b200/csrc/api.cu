@@ -128,7 +128,9 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
 }
 
 // 0 = automatic (= 4), 1 = per-stage kernels, 2 / 3 = fused 32x32 / 32x64 tiles filled with plain loads from
-// interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy
+// interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy, one launch
+// per step, 6 / 7 = as 4 / 5 but the whole time loop in one persistent, neighbour-synchronised launch when
+// every tile is resident at once (experimental: measured slower than per-step launches)
 static std::atomic<int> g_path_2d{0};
 
 // Coefficients shared by every member of the batch (host copy), or null: set by the entry points that
@@ -208,7 +210,7 @@ int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, d
 // ping-pongs between two planar buffers, and the result is interleaved back at the end.
 int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                           const double *pumping, const double *coeffs, double2 *psi, double2 *work, int variant,
-                          cudaStream_t stream)
+                          bool allow_persistent, cudaStream_t stream)
 {
     Fused2DPlanar p;
     p.batch = batch; p.rows = rows; p.cols = cols; p.pitch = planar_pitch(cols);
@@ -220,6 +222,20 @@ int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, d
     PlanarMaps maps;
     NLSB_TRY(make_planar_maps(order, variant, p, &maps));
     NLSB_TRY(launch_split_planar(p, psi, pumping, stream));
+
+    // small grids: every tile resident at once -> the whole time loop in one cooperative launch
+    bool fits = false;
+    long long tiles = 0;
+    if (allow_persistent && iters >= 2) NLSB_TRY(persistent_2d_fits(order, variant, p, &fits, &tiles));
+    if (fits) {
+        Arena mem(stream);
+        int *flags;
+        NLSB_TRY(mem.alloc(&flags, (size_t)tiles));
+        NLSB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)tiles, stream));
+        NLSB_TRY(launch_rk4_persistent_2d_planar(order, variant, p, maps, iters, flags, w, stream));
+        NLSB_TRY(launch_join_planar(p, (iters & 1) != 0, psi, stream));
+        return 0;
+    }
 
     auto steps = [&](int first, int count, cudaStream_t s, int *rc) {
         for (int i = 0; i < count; ++i) {
@@ -270,8 +286,8 @@ int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double d
         return enqueue_rk4_2d_staged(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
     if (path == 2 || path == 3 || batch > 32767 || rows > 65535)
         return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
-    return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, path == 5 ? 1 : 0,
-                                 stream);
+    return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work,
+                                 (path == 5 || path == 7) ? 1 : 0, path == 6 || path == 7, stream);
 }
 
 int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
@@ -442,7 +458,7 @@ unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memo
 
 int nlsb_set_2d_path(int path)
 {
-    if (path < 0 || path > 5) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..5 (fused step)");
+    if (path < 0 || path > 7) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..7 (fused step)");
     g_path_2d.store(path);
     return 0;
 }
@@ -805,7 +821,7 @@ int nlsb_dev_rk4_step_2d_slab_planar(int rows_alloc, int cols, int order, double
     CrossWeights w{};
     NLSB_TRY(weights_from_host(order, wx, wy, &w));
     const RhsCoeffs shared = rhs_coeffs_from(coeffs_host);
-    const int variant = g_path_2d.load() == 5 ? 1 : 0;
+    const int variant = (g_path_2d.load() == 5 || g_path_2d.load() == 7) ? 1 : 0;
     Fused2DPlanar p;
     p.batch = 1; p.rows = rows_alloc; p.cols = cols; p.pitch = planar_pitch(cols);
     p.grow0 = global_row0; p.grows = global_rows; p.out_row0 = out_row0; p.out_row1 = out_row1;

@@ -503,6 +503,116 @@ rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant
     run_stage<C, 4, TMA>(sm, t, c, wx, wy, own, out);
 }
 
+// ---- persistent variant: the whole time loop in ONE launch ------------------------------------------
+// For grids whose tiles all fit on the GPU at once (512^2: 256 CTAs on 148 SMs x 2) every CTA keeps its
+// tile for all steps and synchronises only with its (up to 8) neighbouring tiles through per-tile step
+// counters in global memory: a CTA may start step s once its neighbours have published step s-1 (which
+// also means they no longer read the buffer this CTA is about to overwrite).  No launch gaps, no
+// end-of-kernel tail, neighbours drift freely.  Launched cooperatively so that co-residency -- which the
+// spin-waits rely on -- is guaranteed by the driver; a wait that exceeds ~1 s traps instead of hanging.
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+template <typename C, bool UNIFORM>
+__global__ void __launch_bounds__(C::THREADS, C::MINBLOCKS)
+rk4_persistent_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ WeightsArg<C::K> wa,
+                      const __grid_constant__ TensorMap map_a, const __grid_constant__ TensorMap map_b,
+                      const __grid_constant__ TensorMap map_cp, double *buf_a, double *buf_b, int *flags, int steps)
+{
+    constexpr int K = C::K;
+    extern __shared__ __align__(128) double smem_raw[];
+    Smem<C> sm{smem_raw};
+
+    const int tid = threadIdx.x;
+    const int tile_x = blockIdx.x % a.tiles_x, tile_y = blockIdx.x / a.tiles_x;
+    const size_t member = blockIdx.y;
+    const size_t pplane = (size_t)a.rows * a.pitch;
+    const RhsCoeffs c = UNIFORM ? a.cu : load_rhs_coeffs(a.coeffs + member * 23);
+
+    TileCtx t;
+    t.x0 = tile_x * C::TX - C::HXL;
+    t.y0 = tile_y * C::TY - C::FY0;
+    t.cols = a.cols; t.grow0 = 0; t.grows = a.rows;
+    t.out_row0 = 0; t.out_row1 = a.rows;
+    t.half_dt = a.half_dt; t.dt = a.dt; t.dt6 = a.dt6;
+
+    double wx[2 * K + 1], wy[2 * K + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * K + 1; ++i) { wx[i] = wa.wx[i]; wy[i] = wa.wy[i]; }
+
+    // step counters: one per tile; thread i < 8 watches neighbour i
+    int *my_flag = flags + (member * gridDim.x + blockIdx.x);
+    const int *watch = nullptr;
+    if (tid < 8) {
+        const int d = tid < 4 ? tid : tid + 1;            // skip (0, 0)
+        const int nx = tile_x + d % 3 - 1, ny = tile_y + d / 3 - 1;
+        if (nx >= 0 && nx < a.tiles_x && ny >= 0 && ny < a.tiles_y)
+            watch = flags + (member * gridDim.x + (size_t)ny * a.tiles_x + nx);
+    }
+
+    const uint32_t bar = smem_u32(smem_raw + 2 * C::PLANE0 + 5 * C::PLANE1);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {      // c12*P does not change: fetched once
+        mbar_expect_tx(bar, sizeof(double) * C::W1 * C::H1);
+        tma_load_3d(smem_u32(sm.cp()), &map_cp, bar, t.x0 + C::OX, t.y0 + C::OY, (int)member);
+    }
+    mbar_wait(bar, 0);
+
+    Owned<C::MB> own;
+    for (int s = 0; s < steps; ++s) {
+        if (s > 0 && watch) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(watch) < s)
+                if (clock64() - t0 > 4000000000ll) __trap();   // a neighbour never arrived: fail loudly
+        }
+        __syncthreads();   // neighbours are ready; every warp of this CTA is done with the previous step
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, sizeof(double) * 2 * C::W0 * C::H0);
+            const TensorMap *src = (s & 1) ? &map_b : &map_a;
+            tma_load_3d(smem_u32(sm.re0()), src, bar, t.x0, t.y0, (int)(2 * member));
+            tma_load_3d(smem_u32(sm.im0()), src, bar, t.x0, t.y0, (int)(2 * member + 1));
+        }
+        mbar_wait(bar, (s + 1) & 1);
+
+        OutRef out;
+        double *dst = (s & 1) ? buf_a : buf_b;
+        out.aos = nullptr;
+        out.re = dst + (2 * member) * pplane;
+        out.im = dst + (2 * member + 1) * pplane;
+        out.pitch = a.pitch;
+
+        run_stage<C, 1, true>(sm, t, c, wx, wy, own, out);
+        __syncthreads();
+        run_stage<C, 2, true>(sm, t, c, wx, wy, own, out);
+        __syncthreads();
+        run_stage<C, 3, true>(sm, t, c, wx, wy, own, out);
+        __syncthreads();
+        run_stage<C, 4, true>(sm, t, c, wx, wy, own, out);
+
+        // publish: the CTA barrier orders every thread's stores before thread 0, whose gpu-scope fence
+        // and release store then make them visible (cumulativity) to whoever acquires the counter
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            st_release_gpu(my_flag, s + 1);
+        }
+    }
+}
+
 template <typename C, bool UNIFORM, bool TMA>
 int configure_fused()
 {
@@ -577,6 +687,55 @@ int launch_fused_planar_cfg(const Fused2DPlanar &p, const PlanarMaps &maps, bool
     return (int)cudaGetLastError();
 }
 
+template <typename C, bool UNIFORM>
+int persistent_cfg(const Fused2DPlanar &p, const PlanarMaps *maps, int steps, int *flags, const CrossWeights *w,
+                   cudaStream_t stream, long long *tiles_out, long long *capacity_out)
+{
+    static int capacity[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return fail(NLSB_EINVAL, "device ordinal %d out of range", dev);
+    if (!capacity[dev]) {
+        e = cudaFuncSetAttribute(rk4_persistent_kernel<C, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(rk4_persistent_kernel<C, UNIFORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk4_persistent_kernel<C, UNIFORM>, C::THREADS, C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        capacity[dev] = per_sm * sms > 0 ? per_sm * sms : -1;
+    }
+    const int tiles_x = (p.cols + C::TX - 1) / C::TX, tiles_y = (p.rows + C::TY - 1) / C::TY;
+    *tiles_out = (long long)tiles_x * tiles_y * p.batch;
+    *capacity_out = capacity[dev];
+    if (!maps) return 0;                     // query only
+    if (*tiles_out > *capacity_out) return fail(NLSB_ESIZE, "persistent kernel: %lld tiles exceed the %lld resident CTAs",
+                                                *tiles_out, *capacity_out);
+    FusedArgs a{};
+    a.rows = p.rows; a.cols = p.cols; a.grow0 = 0; a.grows = p.rows; a.out_row0 = 0; a.out_row1 = p.rows;
+    a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+    a.pitch = p.pitch; a.coeffs = p.coeffs;
+    if (UNIFORM) a.cu = *p.uniform;
+    a.dt = p.dt; a.half_dt = p.dt / 2; a.dt6 = p.dt / 6;
+    WeightsArg<C::K> wa = pack_weights<C>(*w);
+    TensorMap ma, mb, mc;
+    std::memcpy(ma.bytes, maps->psi_a, 128);
+    std::memcpy(mb.bytes, maps->psi_b, 128);
+    std::memcpy(mc.bytes, maps->cp, 128);
+    double *buf_a = p.psi_a, *buf_b = p.psi_b;
+    void *args[] = {&a, &wa, &ma, &mb, &mc, &buf_a, &buf_b, &flags, &steps};
+    const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)p.batch);
+    e = cudaLaunchCooperativeKernel((const void *)rk4_persistent_kernel<C, UNIFORM>, grid, dim3(C::THREADS), args, C::SMEM,
+                                    stream);
+    if (e != cudaSuccess) return (int)e;
+    count_launches(1);
+    return 0;
+}
+
 // Tile shapes.  variant 0: 32x32 tiles, 256 threads, two CTAs per SM (one CTA's fill and barriers
 // hide behind the other's arithmetic); variant 1: 32x64 tiles, 512 threads, one CTA per SM (less
 // redundant halo work).
@@ -607,6 +766,30 @@ int launch_fused_planar_k(int variant, const Fused2DPlanar &p, const PlanarMaps 
                          : launch_fused_planar_cfg<Small, false>(p, maps, a_to_b, w, stream);
     return p.uniform ? launch_fused_planar_cfg<Tall, true>(p, maps, a_to_b, w, stream)
                      : launch_fused_planar_cfg<Tall, false>(p, maps, a_to_b, w, stream);
+}
+
+template <int K>
+int persistent_k(int variant, const Fused2DPlanar &p, const PlanarMaps *maps, int steps, int *flags,
+                 const CrossWeights *w, cudaStream_t stream, long long *tiles, long long *capacity)
+{
+    using Small = typename Shapes<K>::Small;
+    using Tall = typename Shapes<K>::Tall;
+    if (K == 3 || variant == 0)
+        return p.uniform ? persistent_cfg<Small, true>(p, maps, steps, flags, w, stream, tiles, capacity)
+                         : persistent_cfg<Small, false>(p, maps, steps, flags, w, stream, tiles, capacity);
+    return p.uniform ? persistent_cfg<Tall, true>(p, maps, steps, flags, w, stream, tiles, capacity)
+                     : persistent_cfg<Tall, false>(p, maps, steps, flags, w, stream, tiles, capacity);
+}
+
+int persistent_dispatch(int order, int variant, const Fused2DPlanar &p, const PlanarMaps *maps, int steps, int *flags,
+                        const CrossWeights *w, cudaStream_t stream, long long *tiles, long long *capacity)
+{
+    switch (order) {
+    case 3: return persistent_k<1>(variant, p, maps, steps, flags, w, stream, tiles, capacity);
+    case 5: return persistent_k<2>(variant, p, maps, steps, flags, w, stream, tiles, capacity);
+    case 7: return persistent_k<3>(variant, p, maps, steps, flags, w, stream, tiles, capacity);
+    }
+    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
 }
 
 // ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----
@@ -696,6 +879,22 @@ int make_planar_maps(int order, int variant, const Fused2DPlanar &p, PlanarMaps 
     case 7: return make_maps_k<3>(variant, p, maps);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
+
+int persistent_2d_fits(int order, int variant, const Fused2DPlanar &p, bool *fits, long long *tiles)
+{
+    long long capacity = 0;
+    int rc = persistent_dispatch(order, variant, p, nullptr, 0, nullptr, nullptr, nullptr, tiles, &capacity);
+    if (rc) return rc;
+    *fits = p.batch <= 65535 && *tiles <= capacity;
+    return 0;
+}
+
+int launch_rk4_persistent_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, int steps,
+                                    int *flags, const CrossWeights &w, cudaStream_t stream)
+{
+    long long tiles = 0, capacity = 0;
+    return persistent_dispatch(order, variant, p, &maps, steps, flags, &w, stream, &tiles, &capacity);
 }
 
 int launch_split_planar(const Fused2DPlanar &p, const double2 *psi, const double *pumping, cudaStream_t stream)

@@ -80,6 +80,11 @@ int launch_join_planar(const Fused2DPlanar &p, bool from_b, double2 *psi, cudaSt
 // one RK4 step A -> B (a_to_b) or B -> A
 int launch_rk4_step_fused_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
                                     const CrossWeights &w, cudaStream_t stream);
+// Persistent variant: `steps` RK4 steps (A -> B -> A ...) in ONE cooperative launch; usable when all tiles
+// are resident at once (persistent_2d_fits).  flags: zeroed device ints, one per tile.
+int persistent_2d_fits(int order, int variant, const Fused2DPlanar &p, bool *fits, long long *tiles);
+int launch_rk4_persistent_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, int steps,
+                                    int *flags, const CrossWeights &w, cudaStream_t stream);
 int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
                            double sign, cudaStream_t stream);
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,

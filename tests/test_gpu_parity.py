@@ -147,7 +147,7 @@ def test_runge_kutta_with_caller_supplied_band(nls):
     assert rel_l2(got, want) <= 1e-10
 
 
-@pytest.fixture(params=["tma32", "tma64", "fused32", "fused64", "staged"])
+@pytest.fixture(params=["tma32", "tma64", "tma32_persistent", "fused32", "fused64", "staged"])
 def path_2d(request):
     """Both 2D implementations (fused whole-step kernel, per-stage kernels) are held to the same bar."""
     from nls_b200.engine import set_2d_path
