@@ -34,6 +34,15 @@ METRIC = "grid-point RK-steps/sec"
 UNIT = "point-steps/s"
 BYTES_PER_POINT_STEP = 40.0      # read psi 16 + read P 8 + write psi 16
 
+# DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
+# `ncu --set full` captures summarised under profiles/ (round 1, default kernels).  C2's working set is
+# L2-resident: the figure is the cold-cache replay ncu measures, in steady state it is ~0.
+NCU_TRAFFIC = {
+    "c2": (6.34e6, "profiles/r1_ncu_tma32_c2_512.txt (cold L2 under ncu; L2-resident in steady state)"),
+    "c4": (2.657e9, "profiles/r1_ncu_tma32_c4_8192.txt"),
+}
+DOMINANT_KERNEL = {1: "rk4_1d_resident (whole time loop, one launch)", 2: "rk4_step_fused_kernel (one RK4 step per launch)"}
+
 ORIG = dict(R=0.0242057488654, gamma=0.0242057488654, g=0.00162178517398, tilde_g=0.0169440242057,
             gamma_R=0.242057488654)
 
@@ -315,6 +324,12 @@ def run_engine(args):
     peak, peak_src = measured_hbm_peak()
     per_gpu_rate = value / world
     achieved = BYTES_PER_POINT_STEP * per_gpu_rate / 1e9
+    launches_per_gpu = max(int(t[2]), 1)
+    # algorithmic bytes of one launch of the dominant kernel and its average duration over the timed region
+    rk_per_launch = iters if w["dim"] == 1 else 1
+    bytes_per_launch = BYTES_PER_POINT_STEP * (points(w) // world if slabs else points(w)) * rk_per_launch
+    dominant_launches = args.steps * (1 if w["dim"] == 1 else iters)
+    traffic = NCU_TRAFFIC.get(name, (None, None)) if args.path == "auto" and not slabs else (None, None)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -328,9 +343,12 @@ def run_engine(args):
                    "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
         "gpu_launches": int(t[2]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes": "40 B per point-step x point-steps per launch (DESIGN.md)",
-                     "per": "GPU"},
+                     "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src,
+                     "kernel": DOMINANT_KERNEL[w["dim"]],
+                     "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "avg_launch_us": 1e3 * dev_ms_max / dominant_launches,
+                     "algorithmic_bytes": "40 B per point-step x point-steps per launch (DESIGN.md 3)",
+                     "per": "GPU", "launches_in_timed_region": launches_per_gpu},
         "wall_s": t_wall,
     }
     if e2e:

@@ -70,7 +70,17 @@ int internal_stream(cudaStream_t *out)
     int dev = 0;
     NLSB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(NLSB_EINVAL, "device ordinal %d out of range", dev);
-    if (!streams[dev]) NLSB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    if (!streams[dev]) {
+        NLSB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+        // keep the stream-ordered scratch allocations of the host entry points cached between calls:
+        // by default the pool hands memory back to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = streams[dev];
     return 0;
 }
