@@ -140,8 +140,16 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
 // 0 = automatic (= 4), 1 = per-stage kernels, 2 / 3 = fused 32x32 / 32x64 tiles filled with plain loads from
 // interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy, one launch
 // per step, 6 / 7 = as 4 / 5 but the whole time loop in one persistent, neighbour-synchronised launch when
-// every tile is resident at once (experimental: measured slower than per-step launches)
+// every tile is resident at once (experimental: measured slower than per-step launches),
+// 8 = streaming strip-marching kernel (stream_2d.cu) on interleaved psi, one launch per step
 static std::atomic<int> g_path_2d{0};
+
+static int launch_interleaved_step(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    const int path = g_path_2d.load();
+    if (path == 8) return launch_rk4_step_stream_2d(order, s, w, stream);
+    return launch_rk4_step_fused_2d(order, path == 3 ? 1 : 0, s, w, stream);
+}
 
 // Coefficients shared by every member of the batch (host copy), or null: set by the entry points that
 // know them so that the fused kernel can read them from its constant bank.
@@ -168,7 +176,7 @@ void enqueue_fused_steps_2d(int batch, int rows, int cols, int order, double dt,
         const bool even = ((first_step + i) & 1) == 0;
         s.in = even ? psi : work;
         s.out = even ? work : psi;
-        int r = launch_rk4_step_fused_2d(order, g_path_2d.load() == 3 ? 1 : 0, s, w, stream);
+        int r = launch_interleaved_step(order, s, w, stream);
         if (r && !*rc) *rc = r;
     }
 }
@@ -294,7 +302,7 @@ int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double d
     const int path = g_path_2d.load();
     if (path == 1)
         return enqueue_rk4_2d_staged(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
-    if (path == 2 || path == 3 || batch > 32767 || rows > 65535)
+    if (path == 2 || path == 3 || path == 8 || batch > 32767 || rows > 65535)
         return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
     return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work,
                                  (path == 5 || path == 7) ? 1 : 0, path == 6 || path == 7, stream);
@@ -468,7 +476,7 @@ unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memo
 
 int nlsb_set_2d_path(int path)
 {
-    if (path < 0 || path > 7) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..7 (fused step)");
+    if (path < 0 || path > 8) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..8 (fused step)");
     g_path_2d.store(path);
     return 0;
 }
@@ -811,7 +819,7 @@ int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, co
     Fused2DStep s{1, rows_alloc, cols, global_row0, global_rows, out_row0, out_row1,
                   reinterpret_cast<const double2 *>(psi_in), reinterpret_cast<double2 *>(psi_out), pumping, nullptr, dt,
                   &shared};
-    NLSB_TRY(launch_rk4_step_fused_2d(order, g_path_2d.load() == 3 ? 1 : 0, s, w, static_cast<cudaStream_t>(stream)));
+    NLSB_TRY(launch_interleaved_step(order, s, w, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -19,10 +19,14 @@ namespace nlsb {
 // within 1 ulp of the correctly rounded quotient.  Precondition: b is a finite, normal number (the
 // reservoir denominator c13 + c14 |psi|^2 is >= c13 = 1 for every model the host layer builds); a zero,
 // infinite or NaN denominator yields NaN where IEEE division would yield +-inf / 0.
-__device__ __forceinline__ double div_fast(double a, double b)
+__host__ __device__ __forceinline__ double div_fast(double a, double b)
 {
     double x;
+#if defined(__CUDA_ARCH__)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(b));
+#else
+    x = 1.0 / b;   // host emulation of the kernels (tests/emu): same refinement, different seed
+#endif
     double e = fma(-b, x, 1.0);
     x = fma(x, e, x);
     e = fma(-b, x, 1.0);
@@ -32,7 +36,7 @@ __device__ __forceinline__ double div_fast(double a, double b)
     return fma(r, x, q);
 }
 
-__device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, double2 u, double lap_re, double lap_im)
+__host__ __device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, double2 u, double lap_re, double lap_im)
 {
     const double usq = fma(u.x, u.x, u.y * u.y);
     const double res = div_fast(cp, fma(c.c14, usq, c.c13));
@@ -44,7 +48,7 @@ __device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, doub
     return v;
 }
 
-__device__ __forceinline__ RhsCoeffs load_rhs_coeffs(const double *__restrict__ coeffs23)
+__host__ __device__ __forceinline__ RhsCoeffs load_rhs_coeffs(const double *__restrict__ coeffs23)
 {
     RhsCoeffs c;
     c.c3 = coeffs23[2];

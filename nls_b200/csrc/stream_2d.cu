@@ -1,0 +1,303 @@
+// stream_2d.cu -- streaming fused RK4 step of the 2D solver for sm_100a: one launch = one RK4 step
+// (runge_kutta_2d, nls.f90:892-899), the field read ONCE and written ONCE (40 B per node-step).
+//
+// A CTA owns a strip of columns and marches down a chunk of rows with the four RK stages skewed by K rows
+// (stream_2d_core.cuh).  psi rows arrive through a ring of TMA batches (cp.async.bulk.tensor over the
+// interleaved complex128 array viewed as a (2, cols, rows, batch) tensor of doubles; rows / columns outside
+// the array arrive as zeros = the reference's truncated band matrix), the pumping is read straight into
+// registers two rows ahead, the new psi is stored with one coalesced 16-byte store per thread and row.
+// One __syncthreads per iteration: a stage ring row is written in iteration `it` and read in it + K.
+//
+// Compared with the tile kernel (fused_2d.cu): y neighbours never touch shared memory, redundant work falls
+// from 1.43 to about 1.12, no planar working copy, no split / join passes.  Needs grids large enough to fill
+// the GPU with (strip, chunk) CTAs; small grids stay on the tile kernel (api.cu chooses).
+
+#include "kernels.h"
+#include "stream_2d_core.cuh"
+
+#include <cuda.h>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+namespace nlsb {
+
+namespace {
+
+using namespace stream2d;
+
+struct StreamArgs {
+    int rows, cols;          // extent of the local arrays
+    int grow0, grows;        // global row of local row 0, global number of rows
+    int out_row0, out_row1;  // local rows [out_row0, out_row1) are written
+    int strips, chunk_rows;
+    const double *pumping;   // [batch][rows][cols]
+    double2 *out;            // [batch][rows][cols]
+    const double *coeffs;    // [batch][23] -- unused when UNIFORM
+    RhsCoeffs cu;
+    double dt;
+};
+
+template <int K>
+struct StreamWeights {
+    double wx[2 * K + 1];
+    double wy[2 * K + 1];
+};
+
+struct TensorMap {
+    alignas(64) unsigned char bytes[128];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <typename C, bool UNIFORM>
+__global__ void __launch_bounds__(C::T, 1)
+rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ StreamWeights<C::K> wa,
+                  const __grid_constant__ TensorMap map)
+{
+    constexpr int K = C::K, U = C::U, RB = C::RB, NB = C::NB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *yr = reinterpret_cast<double2 *>(smem_raw);
+    double2 *ring = reinterpret_cast<double2 *>(smem_raw + C::RING_OFFSET);
+    const uint32_t bar0 = smem_u32(smem_raw + C::BAR_OFFSET);
+
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % a.strips, chunk = blockIdx.x / a.strips;
+    const size_t member = blockIdx.y;
+    const size_t plane = (size_t)a.rows * a.cols;
+    const Chunk g = make_chunk<C>(strip, chunk, a.chunk_rows, a.out_row0, a.out_row1);
+    const Lane<C> L = make_lane<C>(g, tid, ring, yr, a.pumping + member * plane, a.out + member * plane, a.rows, a.cols,
+                                   a.grow0, a.grows, a.dt);
+    RhsCoeffs cl;
+    if (!UNIFORM) cl = load_rhs_coeffs(a.coeffs + member * 23);
+    const RhsCoeffs &c = UNIFORM ? a.cu : cl;
+
+    constexpr uint32_t kBatchBytes = sizeof(double2) * RB * C::T;
+    auto issue = [&](int b) {     // thread 0: request TMA batch b (rows base + b RB ...)
+        const uint32_t bar = bar0 + 8 * (b % NB);
+        mbar_expect_tx(bar, kBatchBytes);
+        tma_load_4d(smem_u32(ring) + (b % NB) * kBatchBytes, &map, bar, 0, g.c0 - C::HALO, g.base + b * RB, (int)member);
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < NB; ++b) mbar_init(bar0 + 8 * b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int b = 0; b < NB && b < g.nbatches; ++b) issue(b);
+    }
+    for (int i = tid; i < 3 * C::YS * C::YP; i += C::T) yr[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    State<C> s;
+    mbar_wait(bar0, 0);
+    march_begin<C>(s, L, g);
+
+    // U = 2 RB: the batch boundaries fall on fixed phases of the unrolled body
+    const double2 *rh = ring + tid, *ro = ring + U * C::T + tid;
+    for (int itb = 0; itb < g.niter; itb += U) {
+#pragma unroll
+        for (int ph = 0; ph < U; ++ph) {
+            const int it = itb + ph;
+            if ((ph + 2 * K) % RB == 0) {          // psi(j + K) is the first row of a new batch
+                const int b = (it + 2 * K) / RB;
+                mbar_wait(bar0 + 8 * (b % NB), (b / NB) & 1);
+            }
+            march_iter<C>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro);
+            __syncthreads();
+            if ((ph + K + 1) % RB == 0 && tid == 0) {   // every row of batch (it + K + 1) / RB - 1 has been consumed
+                const int nb = (it + K + 1) / RB - 1 + NB;
+                // WAR across proxies (generic reads, then the TMA write) is ordered by the barrier above
+                if (nb < g.nbatches) issue(nb);
+            }
+        }
+        const double2 *t = rh; rh = ro; ro = t;
+    }
+}
+
+// ---- tensor maps (driver entry point fetched through the runtime: no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_complex_map(TensorMap *out, const double2 *base, int batch, int rows, int cols, int box_cols, int box_rows)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(NLSB_EINVAL, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {2, (cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {sizeof(double2), (cuuint64_t)cols * sizeof(double2),
+                                   (cuuint64_t)cols * rows * sizeof(double2)};
+    const cuuint32_t box[4] = {2, (cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double2 *>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NLSB_EINVAL, "cuTensorMapEncodeTiled (stream kernel) failed with CUresult %d", (int)r);
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    std::memcpy(out->bytes, &map, 128);
+    return 0;
+}
+
+// The time loop ping-pongs between two buffers: keep the last few encoded maps instead of re-encoding per step.
+struct MapKey {
+    const void *base;
+    int batch, rows, cols, box_cols, box_rows;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && batch == o.batch && rows == o.rows && cols == o.cols && box_cols == o.box_cols &&
+               box_rows == o.box_rows;
+    }
+};
+
+int cached_map(const MapKey &key, TensorMap *out)
+{
+    constexpr int N = 8;
+    static thread_local MapKey keys[N] = {};
+    static thread_local TensorMap maps[N];
+    static thread_local int next = 0;
+    for (int i = 0; i < N; ++i)
+        if (keys[i].base && keys[i] == key) {
+            *out = maps[i];
+            return 0;
+        }
+    int rc = encode_complex_map(out, static_cast<const double2 *>(key.base), key.batch, key.rows, key.cols, key.box_cols,
+                                key.box_rows);
+    if (rc) return rc;
+    keys[next] = key;
+    maps[next] = *out;
+    next = (next + 1) % N;
+    return 0;
+}
+
+template <typename C, bool UNIFORM>
+int configure_stream()
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        configured[dev] = true;
+    }
+    return 0;
+}
+
+template <typename C>
+int chunk_rows_for(int out_rows, int strips, int batch)
+{
+    // about 140 iterations per CTA (a multiple of U): 12 of them fill and drain the stage pipeline.  Shorter
+    // chunks only when that is needed to give every SM a few CTAs.
+    static const int target = [] {
+        const char *e = std::getenv("NLSB_STREAM_ITERS");     // tuning knob: iterations per CTA
+        const int v = e ? std::atoi(e) : 0;
+        return v >= 2 * C::U + 6 * C::K ? v : 140;
+    }();
+    int h = C::chunk_rows(target);
+    const long long want = 4ll * 148;
+    while (h > C::chunk_rows(2 * C::U + 6 * C::K) &&
+           (long long)strips * ((out_rows + h - 1) / h) * batch < want)
+        h = C::chunk_rows((h + 6 * C::K) / 2);
+    return h;
+}
+
+template <typename C, bool UNIFORM>
+int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    int rc = configure_stream<C, UNIFORM>();
+    if (rc) return rc;
+    const int out_rows = s.out_row1 - s.out_row0;
+    if (out_rows <= 0 || s.cols <= 0 || s.batch <= 0) return 0;
+    StreamArgs a{};
+    a.rows = s.rows; a.cols = s.cols; a.grow0 = s.grow0; a.grows = s.grows;
+    a.out_row0 = s.out_row0; a.out_row1 = s.out_row1;
+    a.strips = (s.cols + C::W - 1) / C::W;
+    a.chunk_rows = chunk_rows_for<C>(out_rows, a.strips, s.batch);
+    a.pumping = s.pumping; a.out = s.out; a.coeffs = s.coeffs;
+    if (UNIFORM) a.cu = *s.uniform;
+    a.dt = s.dt;
+    StreamWeights<C::K> wa;
+    for (int i = 0; i < C::NW; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
+    TensorMap map;
+    rc = cached_map(MapKey{s.in, s.batch, s.rows, s.cols, C::T, C::RB}, &map);
+    if (rc) return rc;
+    const int chunks = (out_rows + a.chunk_rows - 1) / a.chunk_rows;
+    const dim3 grid((unsigned)(a.strips * chunks), (unsigned)s.batch);
+    rk4_stream_kernel<C, UNIFORM><<<grid, C::T, C::SMEM, stream>>>(a, wa, map);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+template <int K>
+struct StreamShape {
+    using Wide = Cfg<K, 256>;
+};
+
+template <int K>
+int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    using C = typename StreamShape<K>::Wide;
+    return s.uniform ? launch_stream_cfg<C, true>(s, w, stream) : launch_stream_cfg<C, false>(s, w, stream);
+}
+
+}  // namespace
+
+// CTAs a launch of the streaming kernel would use (api.cu: the path is chosen only when they fill the GPU).
+long long stream_2d_ctas(int order, int batch, int out_rows, int cols)
+{
+    if (order != 5) return 0;
+    using C = StreamShape<2>::Wide;
+    const int strips = (cols + C::W - 1) / C::W;
+    const int h = chunk_rows_for<C>(out_rows, strips, batch);
+    return (long long)strips * ((out_rows + h - 1) / h) * batch;
+}
+
+int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    if (s.batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", s.batch);
+    if ((reinterpret_cast<uintptr_t>(s.in) & 15) != 0) return fail(NLSB_EINVAL, "psi must be 16-byte aligned");
+    switch (order) {
+    case 3: return launch_stream_k<1>(s, w, stream);
+    case 5: return launch_stream_k<2>(s, w, stream);
+    case 7: return launch_stream_k<3>(s, w, stream);
+    }
+    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
+
+}  // namespace nlsb

@@ -1,0 +1,330 @@
+// stream_2d_core.cuh -- per-thread body of the STREAMING fused RK4 step of the 2D solver.
+//
+// Reference semantics: one iteration of runge_kutta_2d (nls.f90:892-899) = four hamiltonian_2d evaluations
+// (:841-870; cross stencil of make_laplacian_2d :297-385; reservoir :829-839) and the update
+// u + (k1 + 2 k2 + 2 k3 + k4) dt/6.
+//
+// Decomposition: a CTA owns a STRIP of W = T - 8K columns and marches down a CHUNK of rows, one row per
+// iteration.  Thread t owns frame column t (the strip plus a 4K-column halo each side).  The four RK stages
+// run skewed by K rows: in iteration `it` (row j = jstart + it)
+//       stage 1 evaluates row j, stage 2 row j-K, stage 3 row j-2K, stage 4 row j-3K,
+// so every y-neighbour a stage needs has been produced by THIS thread (this or an earlier iteration) and
+// lives in a register window; only the 2K x-neighbours of each stage come from shared memory (rings the
+// owning threads publish to).  Per node-step: 4*2K + 1 shared loads and 3 shared stores of 16 bytes, the
+// redundant work is (T / W) * (1 + 6K / H) instead of the tile kernel's 1.43.
+//
+// Register windows are circular with compile-time indices: the march loop is unrolled U = 2(2K+1) times
+// and `ph` = it mod U is a constant in every unrolled copy, so no register is ever moved.
+//     psi, acc, cp : period U     row j+d  <->  index (ph + d + 3K) mod U      (psi: d in [-3K, K])
+//     y2, y3, y4   : period 2K+1  newest row at (ph + 2K), centre at (ph + K), oldest at ph
+// The shared-memory rings use the same periods, so every shared address of an unrolled copy is one of two base
+// registers plus an immediate: stage rings have NW = 2K+1 rows (row written in iteration `it` lives in slot
+// it mod NW and is read K iterations later), the psi ring has 2U rows = 4 TMA batches of NW rows (the row
+// `rel` rows after the first row of batch 0 lives in slot rel mod 2U; `half` = (it / U) mod 2 selects which
+// half of the ring the unrolled copy starts in).
+//
+// The arithmetic of a node (order of the FMA chain of the stencil, stage algebra, domain mask) is the one of
+// fused_2d.cu, so both kernels produce bit-identical fields.
+//
+// This header is compiled for the device (stream_2d.cu) and for the host (tests/emu/stream_emu.cu runs the
+// same body thread by thread so that the indexing can be tested without a GPU).
+#pragma once
+
+#include "device_math.cuh"
+
+#define NLSB_HD __host__ __device__ __forceinline__
+
+namespace nlsb {
+namespace stream2d {
+
+constexpr int kPrefetchP = 2;   // the pumping value of row j + kPrefetchP is requested in iteration j
+
+template <int K_, int T_>
+struct Cfg {
+    static constexpr int K = K_, T = T_;
+    static constexpr int NW = 2 * K_ + 1;       // taps per axis = period of the y windows and of the stage rings
+    static constexpr int U = 2 * NW;            // unroll of the march = period of the psi / acc / cp windows
+    static constexpr int RB = NW, NB = 4;       // rows per TMA batch, batches in the psi ring
+    static constexpr int HALO = 4 * K_;         // frame columns each side of the strip
+    static constexpr int W = T_ - 2 * HALO;     // columns a strip produces
+    static constexpr int RING = RB * NB;        // rows of the psi ring (= 2U)
+    static constexpr int YS = NW;               // rows of a stage ring: written in iteration it, read in it + K
+    static constexpr int YP = T_ + 2 * K_;      // pitch of a stage ring (K pad columns each side)
+    static constexpr int SKEW = 3 * K_;         // rows between stage 1 and stage 4
+    // shared memory: [3 stage rings][psi ring][pad][mbarriers]; a psi x-neighbour read of an edge thread may leave
+    // its row by K elements (into the stage rings below / the pad above): harmless, those threads carry garbage
+    static constexpr size_t YRING_BYTES = sizeof(double2) * YS * YP;
+    static constexpr size_t RING_OFFSET = (3 * YRING_BYTES + 127) / 128 * 128;
+    static constexpr size_t RING_BYTES = sizeof(double2) * RING * T_;
+    static constexpr size_t BAR_OFFSET = RING_OFFSET + RING_BYTES + 128;
+    static constexpr size_t SMEM = BAR_OFFSET + 8 * NB + 64;
+    static_assert(RING == 2 * U, "psi ring = two unrolled march bodies");
+    static_assert(RB >= 2 * K_, "the first TMA batch must hold the 2K rows the march starts from");
+    static_assert((sizeof(double2) * RB * T_) % 128 == 0, "TMA batches must stay 128-byte aligned");
+    static_assert(W > 0, "strip narrower than its halo");
+    static_assert(4 * K_ < U && 3 * K_ + kPrefetchP < U, "windows do not fit their period");
+    // a chunk of H rows takes H + 6K iterations: H is chosen so that this is a multiple of U
+    static constexpr int chunk_rows(int target_iters) { return (target_iters + U - 1) / U * U - 6 * K_; }
+};
+
+// Geometry of one CTA (uniform over its threads).
+struct Chunk {
+    int r0, r1;        // local rows [r0, r1) this CTA produces
+    int jstart;        // row of stage 1 in iteration 0 (= r0 - 3K)
+    int base;          // first row of TMA batch 0 (= jstart - K)
+    int niter;         // iterations (multiple of U)
+    int nbatches;      // TMA batches the march consumes
+    int c0;            // first column of the strip
+};
+
+template <class C>
+NLSB_HD Chunk make_chunk(int strip, int chunk, int rows_per_chunk, int out_row0, int out_row1)
+{
+    Chunk g;
+    g.r0 = out_row0 + chunk * rows_per_chunk;
+    g.r1 = g.r0 + rows_per_chunk < out_row1 ? g.r0 + rows_per_chunk : out_row1;
+    g.jstart = g.r0 - C::SKEW;
+    g.base = g.jstart - C::K;
+    g.niter = (g.r1 - g.r0 + 2 * C::SKEW + C::U - 1) / C::U * C::U;
+    g.nbatches = (g.niter + 2 * C::K + C::RB - 1) / C::RB;   // rows base .. base + niter - 1 + 2K
+    g.c0 = strip * C::W;
+    return g;
+}
+
+// What a thread keeps in registers for the whole march.
+template <class C>
+struct State {
+    double2 psi[C::U], acc[C::U];
+    double cp[C::U];
+    double2 y2[C::NW], y3[C::NW], y4[C::NW];
+    const double *pnext;       // pumping of this column, row j + kPrefetchP
+    double2 *onext;            // output of this column, row j - 3K
+};
+
+// Loop-invariant values of one thread.
+template <class C>
+struct Lane {
+    const double2 *ring;       // psi ring, [RING][T]
+    double2 *yr;               // three stage rings, [3][YS][YP]
+    const double *P;           // the member's pumping, already offset to this thread's column
+    double2 *out;              // the member's output, already offset to this thread's column
+    size_t pitch;              // elements between rows of P / out (= cols)
+    int fx;                    // frame column = thread index
+    int dlo, dspan;            // local rows [dlo, dlo + dspan) lie inside the local array AND the global domain
+    bool col_in;               // the column lies inside the domain
+    bool col_owned;            // ... and inside the strip: this thread writes the new psi
+    double half_dt, dt, dt6;
+};
+
+template <class C>
+NLSB_HD Lane<C> make_lane(const Chunk &g, int tid, const double2 *ring, double2 *yr, const double *P, double2 *out,
+                          int rows, int cols, int grow0, int grows, double dt)
+{
+    Lane<C> L;
+    L.ring = ring;
+    L.yr = yr;
+    L.fx = tid;
+    const int gx = g.c0 - C::HALO + tid;
+    L.col_in = gx >= 0 && gx < cols;
+    L.col_owned = L.col_in && tid >= C::HALO && tid < C::T - C::HALO;
+    L.P = P + (L.col_in ? gx : 0);
+    L.out = out + (L.col_in ? gx : 0);
+    L.pitch = (size_t)cols;
+    L.dlo = grow0 < 0 ? -grow0 : 0;
+    const int dhi = rows < grows - grow0 ? rows : grows - grow0;
+    L.dspan = dhi > L.dlo ? dhi - L.dlo : 0;
+    L.half_dt = dt / 2; L.dt = dt; L.dt6 = dt / 6;
+    return L;
+}
+
+template <class C>
+NLSB_HD bool row_in_domain(const Lane<C> &L, int ly)
+{
+    return (unsigned)(ly - L.dlo) < (unsigned)L.dspan;
+}
+
+// *p when `take`, else 0; `p` may point outside the array when `take` is false (never dereferenced)
+NLSB_HD double load_if(const double *p, bool take)
+{
+    double v = 0.0;
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(v) : "l"(p), "r"((int)take));
+#else
+    if (take) v = *p;
+#endif
+    return v;
+}
+
+NLSB_HD void store_if(double2 *p, double2 v, bool put)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.v2.f64 [%0], {%1, %2};\n\t}"
+                 ::"l"(p), "d"(v.x), "d"(v.y), "r"((int)put) : "memory");
+#else
+    if (put) *p = v;
+#endif
+}
+
+// Cross stencil of one node: y taps from the register window `w` (period PER, centre index CI), x taps from `xn`
+// (xn[K] is the centre).  Order of the chain: the K rows above, the 2K+1 x taps, the K rows below (fused_2d.cu).
+template <class C, int PER>
+NLSB_HD void cross_stencil(const double2 (&w)[PER], int ci, const double2 (&xn)[C::NW], const double (&wx)[C::NW],
+                           const double (&wy)[C::NW], double &lr, double &li)
+{
+    constexpr int K = C::K;
+    lr = wy[0] * w[(ci - K + PER) % PER].x;
+    li = wy[0] * w[(ci - K + PER) % PER].y;
+#pragma unroll
+    for (int d = -K + 1; d < 0; ++d) {
+        lr = fma(wy[d + K], w[(ci + d + PER) % PER].x, lr);
+        li = fma(wy[d + K], w[(ci + d + PER) % PER].y, li);
+    }
+#pragma unroll
+    for (int tp = 0; tp < C::NW; ++tp) {
+        lr = fma(wx[tp], xn[tp].x, lr);
+        li = fma(wx[tp], xn[tp].y, li);
+    }
+#pragma unroll
+    for (int d = 1; d <= K; ++d) {
+        lr = fma(wy[d + K], w[(ci + d) % PER].x, lr);
+        li = fma(wy[d + K], w[(ci + d) % PER].y, li);
+    }
+}
+
+// Values of the window registers before the first iteration: psi rows jstart-K .. jstart+K-1 from TMA batch 0,
+// the pumping of rows jstart .. jstart + kPrefetchP - 1, everything else zero (finite garbage never reaches a
+// node that is kept: see the validity argument in DESIGN.md 3.5).
+template <class C>
+NLSB_HD void march_begin(State<C> &s, const Lane<C> &L, const Chunk &g)
+{
+    constexpr int K = C::K, U = C::U;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        s.psi[i] = make_double2(0.0, 0.0);
+        s.acc[i] = make_double2(0.0, 0.0);
+        s.cp[i] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < C::NW; ++i) s.y2[i] = s.y3[i] = s.y4[i] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int d = -K; d < K; ++d) s.psi[(d + 3 * K) % U] = L.ring[(d + K) * C::T + L.fx];   // it = 0: ring slot = rel
+    s.pnext = L.P + (ptrdiff_t)g.jstart * (ptrdiff_t)L.pitch;
+#pragma unroll
+    for (int d = 0; d < kPrefetchP; ++d) {
+        s.cp[(d + 3 * K) % U] = load_if(s.pnext, L.col_in && row_in_domain(L, g.jstart + d));
+        s.pnext += L.pitch;
+    }
+    s.onext = L.out + (ptrdiff_t)(g.jstart - 3 * K) * (ptrdiff_t)L.pitch;
+}
+
+// Row `rel` (counted from the first row of TMA batch 0) of the psi ring lives in slot rel mod 2U.  An unrolled
+// body starts at it = itb (a multiple of U): with rh = ring + (itb mod 2U) T and ro = the other half, the row
+// rel = itb + srel (srel a compile-time constant in [0, 2U)) is at a constant offset from rh or ro.
+template <class C>
+NLSB_HD const double2 *ring_row(const double2 *rh, const double2 *ro, int srel)
+{
+    return srel < C::U ? rh + srel * C::T : ro + (srel - C::U) * C::T;
+}
+
+// One iteration of the march.  `ph` must equal it mod U, rh / ro are the halves of the psi ring (already offset
+// to this thread's column) as ring_row wants them; in the kernel `ph` is a compile-time constant of the
+// unrolled copy and rh / ro swap once per unrolled body.
+template <class C>
+NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const RhsCoeffs &c, const double (&wx)[C::NW],
+                        const double (&wy)[C::NW], int it, int ph, const double2 *rh, const double2 *ro)
+{
+    constexpr int K = C::K, U = C::U, NW = C::NW, YP = C::YP;
+    const int j = g.jstart + it;
+    const int q = ph % NW;                // stage-ring row written in this iteration
+    const int qr = (ph + NW - K) % NW;    // stage-ring row written K iterations ago
+
+    // ---- loads ---------------------------------------------------------------------------------------
+    s.psi[(ph + 4 * K) % U] = *ring_row<C>(rh, ro, ph + 2 * K);                        // psi(j + K)
+    s.cp[(ph + kPrefetchP + 3 * K) % U] = load_if(s.pnext, L.col_in && row_in_domain(L, j + kPrefetchP));
+    s.pnext += L.pitch;
+    double2 x1[NW], x2[NW], x3[NW], x4[NW];
+    {
+        const double2 *row = ring_row<C>(rh, ro, ph + K);                              // psi(j)
+        const double2 *r2 = L.yr + (0 * C::YS + qr) * YP + K + L.fx;
+        const double2 *r3 = L.yr + (1 * C::YS + qr) * YP + K + L.fx;
+        const double2 *r4 = L.yr + (2 * C::YS + qr) * YP + K + L.fx;
+#pragma unroll
+        for (int tp = -K; tp <= K; ++tp) {
+            if (tp == 0) continue;
+            x1[tp + K] = row[tp];      // edge threads read up to K elements outside their row (see Cfg)
+            x2[tp + K] = r2[tp];
+            x3[tp + K] = r3[tp];
+            x4[tp + K] = r4[tp];
+        }
+    }
+    const bool in1 = L.col_in && row_in_domain(L, j);
+    const bool in2 = L.col_in && row_in_domain(L, j - K);
+    const bool in3 = L.col_in && row_in_domain(L, j - 2 * K);
+
+    // ---- stage 1, row j -------------------------------------------------------------------------------
+    {
+        const int ci = (ph + 3 * K) % U;
+        s.cp[ci] = c.c12 * s.cp[ci];                  // c12 * P, rounded once (nls.f90:580 association)
+        const double2 u = s.psi[ci];
+        x1[K] = u;
+        double lr, li;
+        cross_stencil<C, U>(s.psi, ci, x1, wx, wy, lr, li);
+        const double2 k = rhs_point(c, s.cp[ci], u, lr, li);
+        double2 y;
+        y.x = in1 ? fma(k.x, L.half_dt, u.x) : 0.0;
+        y.y = in1 ? fma(k.y, L.half_dt, u.y) : 0.0;
+        s.acc[ci] = k;
+        s.y2[(ph + 2 * K) % NW] = y;
+        L.yr[(0 * C::YS + q) * YP + K + L.fx] = y;
+    }
+    // ---- stage 2, row j - K ---------------------------------------------------------------------------
+    {
+        const int ci = (ph + K) % NW, cu = (ph + 2 * K) % U;
+        const double2 u = s.y2[ci];
+        x2[K] = u;
+        double lr, li;
+        cross_stencil<C, NW>(s.y2, ci, x2, wx, wy, lr, li);
+        const double2 k = rhs_point(c, s.cp[cu], u, lr, li);
+        double2 y;
+        y.x = in2 ? fma(k.x, L.half_dt, s.psi[cu].x) : 0.0;
+        y.y = in2 ? fma(k.y, L.half_dt, s.psi[cu].y) : 0.0;
+        s.acc[cu].x = fma(2.0, k.x, s.acc[cu].x);
+        s.acc[cu].y = fma(2.0, k.y, s.acc[cu].y);
+        s.y3[(ph + 2 * K) % NW] = y;
+        L.yr[(1 * C::YS + q) * YP + K + L.fx] = y;
+    }
+    // ---- stage 3, row j - 2K --------------------------------------------------------------------------
+    {
+        const int ci = (ph + K) % NW, cu = (ph + K) % U;
+        const double2 u = s.y3[ci];
+        x3[K] = u;
+        double lr, li;
+        cross_stencil<C, NW>(s.y3, ci, x3, wx, wy, lr, li);
+        const double2 k = rhs_point(c, s.cp[cu], u, lr, li);
+        double2 y;
+        y.x = in3 ? fma(k.x, L.dt, s.psi[cu].x) : 0.0;
+        y.y = in3 ? fma(k.y, L.dt, s.psi[cu].y) : 0.0;
+        s.acc[cu].x = fma(2.0, k.x, s.acc[cu].x);
+        s.acc[cu].y = fma(2.0, k.y, s.acc[cu].y);
+        s.y4[(ph + 2 * K) % NW] = y;
+        L.yr[(2 * C::YS + q) * YP + K + L.fx] = y;
+    }
+    // ---- stage 4, row j - 3K: the new psi ----------------------------------------------------------------
+    {
+        const int ci = (ph + K) % NW, cu = ph % U;
+        const int r = j - 3 * K;
+        const double2 u = s.y4[ci];
+        x4[K] = u;
+        double lr, li;
+        cross_stencil<C, NW>(s.y4, ci, x4, wx, wy, lr, li);
+        const double2 k = rhs_point(c, s.cp[cu], u, lr, li);
+        double2 v;
+        v.x = fma(s.acc[cu].x + k.x, L.dt6, s.psi[cu].x);
+        v.y = fma(s.acc[cu].y + k.y, L.dt6, s.psi[cu].y);
+        store_if(s.onext, v, L.col_owned && (unsigned)(r - g.r0) < (unsigned)(g.r1 - g.r0) && row_in_domain(L, r));
+        s.onext += L.pitch;
+    }
+}
+
+}  // namespace stream2d
+}  // namespace nlsb

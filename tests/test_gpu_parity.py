@@ -147,7 +147,7 @@ def test_runge_kutta_with_caller_supplied_band(nls):
     assert rel_l2(got, want) <= 1e-10
 
 
-@pytest.fixture(params=["tma32", "tma64", "tma32_persistent", "fused32", "fused64", "staged"])
+@pytest.fixture(params=["tma32", "tma64", "tma32_persistent", "fused32", "fused64", "stream", "staged"])
 def path_2d(request):
     """Both 2D implementations (fused whole-step kernel, per-stage kernels) are held to the same bar."""
     from nls_b200.engine import set_2d_path
@@ -179,6 +179,46 @@ def test_fused_and_staged_paths_agree(nls):
     finally:
         set_2d_path("auto")
     assert rel_l2(a, b) <= 1e-13
+
+
+@pytest.mark.parametrize("order,n,iters", [(5, 700, 3), (5, 513, 4), (3, 300, 5), (7, 260, 3), (5, 241, 2)])
+def test_stream_kernel_is_bitwise_equal_to_tile_kernel(nls, order, n, iters):
+    """The strip-marching kernel (several strips and chunks, ragged edges) performs each node's arithmetic in the
+    same order as the tile kernel: identical bits, and both within 1e-10 of the oracle."""
+    from nls_b200.engine import set_2d_path
+    m = model_2d(n, iters, order=order)
+    rng = np.random.default_rng(n)
+    P = m.getPumping() * (1.0 + 0.5 * rng.random((n, n)))
+    args = (m.dt, m.dx, order, iters, P, m.getCoefficients(), rough_field((n, n), n + 1) * 0.05 + 0.1)
+    try:
+        set_2d_path("stream")
+        a = nls.solve_nls_2d(*args)
+        set_2d_path("fused32")
+        b = nls.solve_nls_2d(*args)
+    finally:
+        set_2d_path("auto")
+    assert np.array_equal(a, b)
+    assert rel_l2(a, O.dp.solve_nls_2d(*args)) <= 1e-10
+
+
+def test_stream_kernel_batch_with_member_coefficients(nls):
+    from nls_b200.engine import Grid2D, set_2d_path
+    from nls_b200.model import dimensionless_coefficients
+    n, iters = 300, 6
+    ms = [model_2d(n, iters, radius=r) for r in (3.0, 5.0, 7.5)]
+    P = np.array([m.getPumping() for m in ms])
+    c = np.array([dimensionless_coefficients(dict(ORIG, gamma_R=g)) for g in (0.1, 0.242057488654, 0.7)])
+    out = {}
+    try:
+        for path in ("stream", "fused32"):
+            set_2d_path(path)
+            out[path] = Grid2D(n, 0.1, 1e-3, order=5, batch=3, pumping=P, coeffs=c, u0=0.1).advance(iters).solution()
+    finally:
+        set_2d_path("auto")
+    assert np.array_equal(out["stream"], out["fused32"])
+    for b, m in enumerate(ms):
+        want = O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, P[b], c[b], m.getInitialSolution())
+        assert rel_l2(out["stream"][b], want) <= 1e-10
 
 
 def test_solve_2d_nonsymmetric_input_keeps_index_convention(nls):
