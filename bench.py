@@ -39,9 +39,12 @@ BYTES_PER_POINT_STEP = 40.0      # read psi 16 + read P 8 + write 
 # L2-resident: the figure is the cold-cache replay ncu measures, in steady state it is ~0.
 NCU_TRAFFIC = {
     "c2": (6.34e6, "profiles/r1_ncu_tma32_c2_512.txt (cold L2 under ncu; L2-resident in steady state)"),
-    "c4": (2.657e9, "profiles/r1_ncu_tma32_c4_8192.txt"),
+    "c4": (2.714e9, "profiles/r1_ncu_stream_c4_8192.txt"),
 }
-DOMINANT_KERNEL = {1: "rk4_1d_resident (whole time loop, one launch)", 2: "rk4_step_fused_kernel (one RK4 step per launch)"}
+DOMINANT_KERNEL = {"c1": "rk4_1d_resident (whole time loop, one launch)", "c3": "rk4_1d_resident (whole time loop, one launch)",
+                   "c2": "rk4_step_fused_kernel (TMA tile kernel, one RK4 step per launch)",
+                   "c4": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)",
+                   "c5": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)"}
 
 ORIG = dict(R=0.0242057488654, gamma=0.0242057488654, g=0.00162178517398, tilde_g=0.0169440242057,
             gamma_R=0.242057488654)
@@ -56,7 +59,7 @@ WORKLOADS = {
 }
 
 
-def build_inputs(name, iters=None, batch=None):
+def build_inputs(name, iters=None, batch=None, n=None):
     """Synthetic inputs of the named shape (deterministic)."""
     from nls_b200.model import Problem, dimensionless_coefficients
     from nls_b200.pumping import GaussianRingPumping1D, GaussianRingPumping2D
@@ -65,6 +68,9 @@ def build_inputs(name, iters=None, batch=None):
         w["iters"] = iters
     if batch:
         w["batch"] = batch
+    if n:
+        w["n"] = n
+        w["desc"] += " [n overridden: %d]" % n
     n, B = w["n"], w["batch"]
     coeffs = dimensionless_coefficients(dict(ORIG))
     if name == "c1":
@@ -235,7 +241,7 @@ def run_engine(args):
     batch = None
     if args.batch:
         batch = args.batch
-    w = build_inputs(name, args.iters, batch)
+    w = build_inputs(name, args.iters, batch, args.n)
     if shard:
         lo, hi = rank * w["batch"] // world, (rank + 1) * w["batch"] // world
         for key in ("pumping", "coeffs", "u0"):
@@ -318,7 +324,7 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
 
-    total_points = points(build_inputs(name, args.iters, batch)) if shard else points(w) * (1 if slabs else world)
+    total_points = points(build_inputs(name, args.iters, batch, args.n)) if shard else points(w) * (1 if slabs else world)
     work = float(total_points) * iters * args.steps
     value = work / (dev_ms_max * 1e-3)
     peak, peak_src = measured_hbm_peak()
@@ -344,7 +350,7 @@ def run_engine(args):
         "gpu_launches": int(t[2]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src,
-                     "kernel": DOMINANT_KERNEL[w["dim"]],
+                     "kernel": DOMINANT_KERNEL[name],
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "avg_launch_us": 1e3 * dev_ms_max / dominant_launches,
                      "algorithmic_bytes": "40 B per point-step x point-steps per launch (DESIGN.md 3)",
@@ -381,6 +387,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
+    ap.add_argument("--n", type=int, default=None, help="override the grid size (profiling only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "staged"], default="auto", help="2D kernel family")
     args = ap.parse_args()

@@ -141,13 +141,21 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
 // interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy, one launch
 // per step, 6 / 7 = as 4 / 5 but the whole time loop in one persistent, neighbour-synchronised launch when
 // every tile is resident at once (experimental: measured slower than per-step launches),
-// 8 = streaming strip-marching kernel (stream_2d.cu) on interleaved psi, one launch per step
+// 8 = streaming strip-marching kernel (stream_2d.cu) on interleaved psi, one launch per step.
+// Automatic: the streaming kernel for launches of at least 2^20 nodes (measured on B200: 1.0x the tile kernel at
+// 1024^2, 1.5x at 2048^2, 1.56x at 8192^2), the TMA tile kernel below that.  Both produce the same bits.
 static std::atomic<int> g_path_2d{0};
+
+static bool stream_preferred(int order, int batch, int out_rows, int cols)
+{
+    return (order == 3 || order == 5) && (cols & 1) == 0 && (long long)batch * out_rows * cols >= (1ll << 20);
+}
 
 static int launch_interleaved_step(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
 {
     const int path = g_path_2d.load();
-    if (path == 8) return launch_rk4_step_stream_2d(order, s, w, stream);
+    if (path == 8 || (path == 0 && stream_preferred(order, s.batch, s.out_row1 - s.out_row0, s.cols)))
+        return launch_rk4_step_stream_2d(order, s, w, stream);
     return launch_rk4_step_fused_2d(order, path == 3 ? 1 : 0, s, w, stream);
 }
 
@@ -302,7 +310,8 @@ int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double d
     const int path = g_path_2d.load();
     if (path == 1)
         return enqueue_rk4_2d_staged(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
-    if (path == 2 || path == 3 || path == 8 || batch > 32767 || rows > 65535)
+    if (path == 2 || path == 3 || path == 8 || batch > 32767 || rows > 65535 ||
+        (path == 0 && stream_preferred(order, batch, rows, cols)))
         return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
     return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work,
                                  (path == 5 || path == 7) ? 1 : 0, path == 6 || path == 7, stream);

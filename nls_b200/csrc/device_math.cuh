@@ -36,16 +36,29 @@ __host__ __device__ __forceinline__ double div_fast(double a, double b)
     return fma(r, x, q);
 }
 
-__host__ __device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, double2 u, double lap_re, double lap_im)
+// The two halves of rhs_point: the coefficients a, b depend on the node's own value only (they can be formed
+// before the node's neighbours are known), the second half folds in the Laplacian.
+__host__ __device__ __forceinline__ void rhs_ab(const RhsCoeffs &c, double cp, double2 u, double &a, double &b)
 {
     const double usq = fma(u.x, u.x, u.y * u.y);
     const double res = div_fast(cp, fma(c.c14, usq, c.c13));
-    const double a = fma(c.c3, res, -c.c4);
-    const double b = fma(c.c5, usq, c.c6 * res);
+    a = fma(c.c3, res, -c.c4);
+    b = fma(c.c5, usq, c.c6 * res);
+}
+
+__host__ __device__ __forceinline__ double2 rhs_apply(double a, double b, double2 u, double lap_re, double lap_im)
+{
     double2 v;
     v.x = fma(a, u.x, fma(b, u.y, -lap_im));
     v.y = fma(a, u.y, fma(-b, u.x, lap_re));
     return v;
+}
+
+__host__ __device__ __forceinline__ double2 rhs_point(const RhsCoeffs &c, double cp, double2 u, double lap_re, double lap_im)
+{
+    double a, b;
+    rhs_ab(c, cp, u, a, b);
+    return rhs_apply(a, b, u, lap_re, lap_im);
 }
 
 __host__ __device__ __forceinline__ RhsCoeffs load_rhs_coeffs(const double *__restrict__ coeffs23)

@@ -53,9 +53,8 @@ struct Fused2DStep {
 // variant 0: 32x32 tiles, two CTAs per SM; variant 1: 32x64 tiles, one CTA of 512 threads per SM
 int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
 // stream_2d.cu: the same step as a strip-marching kernel (skewed stages, register windows, TMA row ring); reads
-// and writes interleaved psi.  stream_2d_ctas: CTAs a launch would use (0 when the order has no streaming kernel).
+// and writes interleaved psi (grids with an odd number of columns are handed to the tile kernel: same bits).
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
-long long stream_2d_ctas(int order, int batch, int out_rows, int cols);
 // Planar (re-plane / im-plane) working copy of psi used by the whole-grid time loop: lets the fused
 // kernel fetch its frames with TMA (cp.async.bulk.tensor, out-of-bounds zero fill = the truncated
 // stencil boundary).  Layout: psi planes [batch][2][rows][pitch], c12*P [batch][rows][pitch], pitch even.

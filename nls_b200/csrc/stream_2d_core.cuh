@@ -37,8 +37,6 @@
 namespace nlsb {
 namespace stream2d {
 
-constexpr int kPrefetchP = 2;   // the pumping value of row j + kPrefetchP is requested in iteration j
-
 template <int K_, int T_>
 struct Cfg {
     static constexpr int K = K_, T = T_;
@@ -51,18 +49,21 @@ struct Cfg {
     static constexpr int YS = NW;               // rows of a stage ring: written in iteration it, read in it + K
     static constexpr int YP = T_ + 2 * K_;      // pitch of a stage ring (K pad columns each side)
     static constexpr int SKEW = 3 * K_;         // rows between stage 1 and stage 4
-    // shared memory: [3 stage rings][psi ring][pad][mbarriers]; a psi x-neighbour read of an edge thread may leave
-    // its row by K elements (into the stage rings below / the pad above): harmless, those threads carry garbage
+    // shared memory: [3 stage rings][psi ring][pumping ring][mbarriers]; a psi x-neighbour read of an edge thread
+    // may leave its row by K elements (into the stage rings below / the pumping ring above): harmless, those
+    // threads carry garbage
     static constexpr size_t YRING_BYTES = sizeof(double2) * YS * YP;
     static constexpr size_t RING_OFFSET = (3 * YRING_BYTES + 127) / 128 * 128;
     static constexpr size_t RING_BYTES = sizeof(double2) * RING * T_;
-    static constexpr size_t BAR_OFFSET = RING_OFFSET + RING_BYTES + 128;
+    static constexpr size_t PRING_OFFSET = RING_OFFSET + RING_BYTES;
+    static constexpr size_t PRING_BYTES = sizeof(double) * RING * T_;
+    static constexpr size_t BAR_OFFSET = PRING_OFFSET + PRING_BYTES;
     static constexpr size_t SMEM = BAR_OFFSET + 8 * NB + 64;
     static_assert(RING == 2 * U, "psi ring = two unrolled march bodies");
     static_assert(RB >= 2 * K_, "the first TMA batch must hold the 2K rows the march starts from");
-    static_assert((sizeof(double2) * RB * T_) % 128 == 0, "TMA batches must stay 128-byte aligned");
+    static_assert((sizeof(double) * RB * T_) % 128 == 0, "TMA batches must stay 128-byte aligned");
     static_assert(W > 0, "strip narrower than its halo");
-    static_assert(4 * K_ < U && 3 * K_ + kPrefetchP < U, "windows do not fit their period");
+    static_assert(4 * K_ < U, "windows do not fit their period");
     // a chunk of H rows takes H + 6K iterations: H is chosen so that this is a multiple of U
     static constexpr int chunk_rows(int target_iters) { return (target_iters + U - 1) / U * U - 6 * K_; }
 };
@@ -97,7 +98,6 @@ struct State {
     double2 psi[C::U], acc[C::U];
     double cp[C::U];
     double2 y2[C::NW], y3[C::NW], y4[C::NW];
-    const double *pnext;       // pumping of this column, row j + kPrefetchP
     double2 *onext;            // output of this column, row j - 3K
 };
 
@@ -106,7 +106,6 @@ template <class C>
 struct Lane {
     const double2 *ring;       // psi ring, [RING][T]
     double2 *yr;               // three stage rings, [3][YS][YP]
-    const double *P;           // the member's pumping, already offset to this thread's column
     double2 *out;              // the member's output, already offset to this thread's column
     size_t pitch;              // elements between rows of P / out (= cols)
     int fx;                    // frame column = thread index
@@ -117,8 +116,8 @@ struct Lane {
 };
 
 template <class C>
-NLSB_HD Lane<C> make_lane(const Chunk &g, int tid, const double2 *ring, double2 *yr, const double *P, double2 *out,
-                          int rows, int cols, int grow0, int grows, double dt)
+NLSB_HD Lane<C> make_lane(const Chunk &g, int tid, const double2 *ring, double2 *yr, double2 *out, int rows, int cols,
+                          int grow0, int grows, double dt)
 {
     Lane<C> L;
     L.ring = ring;
@@ -127,7 +126,6 @@ NLSB_HD Lane<C> make_lane(const Chunk &g, int tid, const double2 *ring, double2 
     const int gx = g.c0 - C::HALO + tid;
     L.col_in = gx >= 0 && gx < cols;
     L.col_owned = L.col_in && tid >= C::HALO && tid < C::T - C::HALO;
-    L.P = P + (L.col_in ? gx : 0);
     L.out = out + (L.col_in ? gx : 0);
     L.pitch = (size_t)cols;
     L.dlo = grow0 < 0 ? -grow0 : 0;
@@ -141,18 +139,6 @@ template <class C>
 NLSB_HD bool row_in_domain(const Lane<C> &L, int ly)
 {
     return (unsigned)(ly - L.dlo) < (unsigned)L.dspan;
-}
-
-// *p when `take`, else 0; `p` may point outside the array when `take` is false (never dereferenced)
-NLSB_HD double load_if(const double *p, bool take)
-{
-    double v = 0.0;
-#if defined(__CUDA_ARCH__)
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "+d"(v) : "l"(p), "r"((int)take));
-#else
-    if (take) v = *p;
-#endif
-    return v;
 }
 
 NLSB_HD void store_if(double2 *p, double2 v, bool put)
@@ -192,8 +178,8 @@ NLSB_HD void cross_stencil(const double2 (&w)[PER], int ci, const double2 (&xn)[
 }
 
 // Values of the window registers before the first iteration: psi rows jstart-K .. jstart+K-1 from TMA batch 0,
-// the pumping of rows jstart .. jstart + kPrefetchP - 1, everything else zero (finite garbage never reaches a
-// node that is kept: see the validity argument in DESIGN.md 3.5).
+// everything else zero (finite garbage never reaches a node that is kept: see the validity argument in
+// DESIGN.md 3.5).
 template <class C>
 NLSB_HD void march_begin(State<C> &s, const Lane<C> &L, const Chunk &g)
 {
@@ -208,30 +194,25 @@ NLSB_HD void march_begin(State<C> &s, const Lane<C> &L, const Chunk &g)
     for (int i = 0; i < C::NW; ++i) s.y2[i] = s.y3[i] = s.y4[i] = make_double2(0.0, 0.0);
 #pragma unroll
     for (int d = -K; d < K; ++d) s.psi[(d + 3 * K) % U] = L.ring[(d + K) * C::T + L.fx];   // it = 0: ring slot = rel
-    s.pnext = L.P + (ptrdiff_t)g.jstart * (ptrdiff_t)L.pitch;
-#pragma unroll
-    for (int d = 0; d < kPrefetchP; ++d) {
-        s.cp[(d + 3 * K) % U] = load_if(s.pnext, L.col_in && row_in_domain(L, g.jstart + d));
-        s.pnext += L.pitch;
-    }
     s.onext = L.out + (ptrdiff_t)(g.jstart - 3 * K) * (ptrdiff_t)L.pitch;
 }
 
 // Row `rel` (counted from the first row of TMA batch 0) of the psi ring lives in slot rel mod 2U.  An unrolled
 // body starts at it = itb (a multiple of U): with rh = ring + (itb mod 2U) T and ro = the other half, the row
 // rel = itb + srel (srel a compile-time constant in [0, 2U)) is at a constant offset from rh or ro.
-template <class C>
-NLSB_HD const double2 *ring_row(const double2 *rh, const double2 *ro, int srel)
+template <class C, class E>
+NLSB_HD const E *ring_row(const E *rh, const E *ro, int srel)
 {
     return srel < C::U ? rh + srel * C::T : ro + (srel - C::U) * C::T;
 }
 
-// One iteration of the march.  `ph` must equal it mod U, rh / ro are the halves of the psi ring (already offset
-// to this thread's column) as ring_row wants them; in the kernel `ph` is a compile-time constant of the
-// unrolled copy and rh / ro swap once per unrolled body.
+// One iteration of the march.  `ph` must equal it mod U, rh / ro are the halves of the psi ring and ph_ / po_ of
+// the pumping ring (already offset to this thread's column) as ring_row wants them; in the kernel `ph` is a
+// compile-time constant of the unrolled copy and the halves swap once per unrolled body.
 template <class C>
 NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const RhsCoeffs &c, const double (&wx)[C::NW],
-                        const double (&wy)[C::NW], int it, int ph, const double2 *rh, const double2 *ro)
+                        const double (&wy)[C::NW], int it, int ph, const double2 *rh, const double2 *ro, const double *ph_,
+                        const double *po_)
 {
     constexpr int K = C::K, U = C::U, NW = C::NW, YP = C::YP;
     const int j = g.jstart + it;
@@ -240,8 +221,6 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
 
     // ---- loads ---------------------------------------------------------------------------------------
     s.psi[(ph + 4 * K) % U] = *ring_row<C>(rh, ro, ph + 2 * K);                        // psi(j + K)
-    s.cp[(ph + kPrefetchP + 3 * K) % U] = load_if(s.pnext, L.col_in && row_in_domain(L, j + kPrefetchP));
-    s.pnext += L.pitch;
     double2 x1[NW], x2[NW], x3[NW], x4[NW];
     {
         const double2 *row = ring_row<C>(rh, ro, ph + K);                              // psi(j)
@@ -264,7 +243,7 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
     // ---- stage 1, row j -------------------------------------------------------------------------------
     {
         const int ci = (ph + 3 * K) % U;
-        s.cp[ci] = c.c12 * s.cp[ci];                  // c12 * P, rounded once (nls.f90:580 association)
+        s.cp[ci] = c.c12 * *ring_row<C>(ph_, po_, ph + K);    // c12 * P(j), rounded once (nls.f90:580 association)
         const double2 u = s.psi[ci];
         x1[K] = u;
         double lr, li;

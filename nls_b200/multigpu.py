@@ -112,6 +112,35 @@ def _cuda_stepper(plan, cols, dx, dt, order, coeffs):
     return step
 
 
+def _cuda_stepper_interleaved(plan, cols, dx, dt, order, coeffs):
+    """One fused RK4 step of a row range on interleaved complex128 slabs (C ABI ``nlsb_dev_rk4_step_2d_slab``).
+    The library sends large row ranges to the strip-marching kernel and thin boundary strips to the tile kernel;
+    both perform a node's arithmetic identically, so the mix does not change a bit of the result."""
+    from . import _lib
+    from .engine import cross_weights
+    wx, wy = cross_weights(order, dx)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+
+    def step(psi_in, psi_out, pumping, row0, row1):
+        _lib.call("nlsb_dev_rk4_step_2d_slab", plan.rows_alloc, cols, order, float(dt),
+                  wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p), plan.global_row0, plan.n,
+                  int(row0), int(row1), C.c_void_p(pumping.data_ptr()), coeffs.ctypes.data_as(C.c_void_p),
+                  C.c_void_p(psi_in.data_ptr()), C.c_void_p(psi_out.data_ptr()),
+                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    step.keepalive = (wx, wy, coeffs)
+    step.planar = False
+    return step
+
+
+def _default_cuda_stepper(plan, cols, dx, dt, order, coeffs):
+    # slabs large enough for the strip-marching kernel (api.cu: stream_preferred) use the interleaved layout
+    lo, hi = plan.owned
+    if order in (3, 5) and cols % 2 == 0 and (hi - lo) * cols >= (1 << 20):
+        return _cuda_stepper_interleaved(plan, cols, dx, dt, order, coeffs)
+    return _cuda_stepper(plan, cols, dx, dt, order, coeffs)
+
+
 class SlabGrid2D(object):
     """One n x n grid advanced by `world` ranks, each owning a slab of rows (BASELINE config 4).
 
@@ -139,7 +168,7 @@ class SlabGrid2D(object):
         self.on_gpu = self.device.type == "cuda"
         p = self.plan
         if stepper is None:
-            stepper = _cuda_stepper
+            stepper = _default_cuda_stepper
         self.stepper = stepper(p, n, dx, dt, order, self.coeffs)
         self.planar = bool(getattr(self.stepper, "planar", False))
         pumping_buf = torch.zeros((p.rows_alloc, n), dtype=torch.float64, device=self.device)

@@ -12,14 +12,20 @@ using namespace nlsb;
 using namespace nlsb::stream2d;
 
 template <class C>
-static void fill_batch(double2 *ring, const Chunk &g, int b, const double2 *in, int rows, int cols)
+static void fill_batch(double2 *ring, double *pring, const Chunk &g, int b, const double2 *in, const double *P, int rows,
+                       int cols)
 {
     for (int r = 0; r < C::RB; ++r)
         for (int x = 0; x < C::T; ++x) {
             const int ly = g.base + b * C::RB + r, lx = g.c0 - C::HALO + x;
             double2 v = make_double2(0.0, 0.0);
-            if (ly >= 0 && ly < rows && lx >= 0 && lx < cols) v = in[(size_t)ly * cols + lx];
+            double p = 0.0;
+            if (ly >= 0 && ly < rows && lx >= 0 && lx < cols) {
+                v = in[(size_t)ly * cols + lx];
+                p = P[(size_t)ly * cols + lx];
+            }
             ring[((b % C::NB) * C::RB + r) * C::T + x] = v;
+            pring[((b % C::NB) * C::RB + r) * C::T + x] = p;
         }
 }
 
@@ -38,12 +44,13 @@ static int run(int rows, int cols, int grow0, int grows, int out_row0, int out_r
             // K pad elements each side: edge threads read x neighbours outside their row (as in the kernel's layout)
             std::vector<double2> ring_store((size_t)C::RING * C::T + 2 * C::K, make_double2(1e300, 1e300));
             double2 *ring = ring_store.data() + C::K;
+            std::vector<double> pring((size_t)C::RING * C::T, 1e300);
             std::vector<double2> yr((size_t)3 * C::YS * C::YP, make_double2(0.0, 0.0));
             std::vector<State<C>> st(C::T);
             std::vector<Lane<C>> lane(C::T);
-            for (int b = 0; b < C::NB && b < g.nbatches; ++b) fill_batch<C>(ring, g, b, in, rows, cols);
+            for (int b = 0; b < C::NB && b < g.nbatches; ++b) fill_batch<C>(ring, pring.data(), g, b, in, P, rows, cols);
             for (int t = 0; t < C::T; ++t) {
-                lane[t] = make_lane<C>(g, t, ring, yr.data(), P, out, rows, cols, grow0, grows, dt);
+                lane[t] = make_lane<C>(g, t, ring, yr.data(), out, rows, cols, grow0, grows, dt);
                 march_begin<C>(st[t], lane[t], g);
             }
             int highest_waited = 0;
@@ -55,11 +62,12 @@ static int run(int rows, int cols, int grow0, int grows, int out_row0, int out_r
                 for (int t = 0; t < C::T; ++t) {
                     const int half = (it / C::U) & 1;
                     march_iter<C>(st[t], lane[t], g, c, wx, wy, it, it % C::U, ring + half * C::U * C::T + t,
-                                  ring + (half ^ 1) * C::U * C::T + t);
+                                  ring + (half ^ 1) * C::U * C::T + t, pring.data() + half * C::U * C::T + t,
+                                  pring.data() + (half ^ 1) * C::U * C::T + t);
                 }
                 if ((it + C::K + 1) % C::RB == 0) {
                     const int nb = (it + C::K + 1) / C::RB - 1 + C::NB;
-                    if (nb < g.nbatches) fill_batch<C>(ring, g, nb, in, rows, cols);
+                    if (nb < g.nbatches) fill_batch<C>(ring, pring.data(), g, nb, in, P, rows, cols);
                 }
             }
         }
@@ -81,7 +89,7 @@ extern "C" int emu_stream_step(int order, int threads, int rows, int cols, int g
     }
     EMU_CASE(1, 256)
     EMU_CASE(2, 256)
-    EMU_CASE(3, 256)
+    EMU_CASE(3, 192)
     EMU_CASE(1, 64)
     EMU_CASE(2, 64)
     EMU_CASE(3, 64)
