@@ -389,7 +389,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
     ap.add_argument("--n", type=int, default=None, help="override the grid size (profiling only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "staged"], default="auto", help="2D kernel family")
+    ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "resident", "staged"], default="auto", help="2D kernel family")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

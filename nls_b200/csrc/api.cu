@@ -141,7 +141,9 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
 // interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy, one launch
 // per step, 6 / 7 = as 4 / 5 but the whole time loop in one persistent, neighbour-synchronised launch when
 // every tile is resident at once (experimental: measured slower than per-step launches),
-// 8 = streaming strip-marching kernel (stream_2d.cu) on interleaved psi, one launch per step.
+// 8 = streaming strip-marching kernel (stream_2d.cu) on interleaved psi, one launch per step,
+// 9 = resident kernel (resident_2d.cu): the whole time loop in one cooperative launch, field in registers,
+//     for grids whose patches are all resident at once (falls back to 4 otherwise).
 // Automatic: the streaming kernel for launches of at least 2^20 nodes (measured on B200: 1.0x the tile kernel at
 // 1024^2, 1.5x at 2048^2, 1.56x at 8192^2), the TMA tile kernel below that.  Both produce the same bits.
 static std::atomic<int> g_path_2d{0};
@@ -304,10 +306,45 @@ int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, d
     return 0;
 }
 
+// Resident path: returns 0 and sets *done when the grid fits and the launch was enqueued.
+int try_rk4_2d_resident(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
+                        const double *pumping, const double *coeffs, double2 *psi, cudaStream_t stream, bool *done)
+{
+    *done = false;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NLSB_CUDA(cudaStreamIsCapturing(stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone || iters < 1) return 0;
+    Resident2D r{batch, rows, cols, iters, psi, pumping, coeffs, g_uniform_coeffs, nullptr, 0u, dt};
+    bool fits = false;
+    size_t bytes = 0;
+    NLSB_TRY(resident_2d_query(order, r, &fits, &bytes));
+    if (!fits) return 0;
+    Arena mem(stream);
+    char *mail;
+    NLSB_TRY(mem.alloc(&mail, bytes));
+    NLSB_CUDA(cudaMemsetAsync(mail, 0, bytes, stream));
+    r.mailbox = mail;
+    // sequence numbers are 32-bit and start from 0 in a fresh mailbox: split very long horizons
+    const int most = 1 << 28;
+    for (int left = iters; left > 0;) {
+        r.steps = left < most ? left : most;
+        NLSB_TRY(launch_rk4_resident_2d(order, r, w, stream));
+        left -= r.steps;
+        if (left > 0) NLSB_CUDA(cudaMemsetAsync(mail, 0, bytes, stream));
+    }
+    *done = true;
+    return 0;
+}
+
 int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                    const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
 {
     const int path = g_path_2d.load();
+    if (path == 9) {
+        bool done = false;
+        NLSB_TRY(try_rk4_2d_resident(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, stream, &done));
+        if (done) return 0;
+    }
     if (path == 1)
         return enqueue_rk4_2d_staged(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
     if (path == 2 || path == 3 || path == 8 || batch > 32767 || rows > 65535 ||
@@ -485,7 +522,7 @@ unsigned long long nlsb_kernel_launches(void) { return g_launches.load(std::memo
 
 int nlsb_set_2d_path(int path)
 {
-    if (path < 0 || path > 8) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..8 (fused step)");
+    if (path < 0 || path > 9) return fail(NLSB_EINVAL, "2D path must be 0 (auto), 1 (per-stage) or 2..9 (fused step)");
     g_path_2d.store(path);
     return 0;
 }

@@ -55,6 +55,23 @@ int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const
 // stream_2d.cu: the same step as a strip-marching kernel (skewed stages, register windows, TMA row ring); reads
 // and writes interleaved psi (grids with an odd number of columns are handed to the tile kernel: same bits).
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
+// resident_2d.cu: `steps` RK4 steps of a SMALL grid in one cooperative launch, psi updated in place; the field
+// lives in registers (one patch per CTA), neighbouring CTAs exchange edge nodes through `mailbox` (device scratch
+// of the size resident_2d_query reports, zero-filled before its first use).  Packets carry sequence numbers
+// seq0 + 1 ... seq0 + 4 steps: a mailbox may be reused by later launches with seq0 advanced accordingly.
+struct Resident2D {
+    int batch, rows, cols;
+    int steps;
+    double2 *psi;
+    const double *pumping;
+    const double *coeffs;       // [batch][23] on the device
+    const RhsCoeffs *uniform;   // host: non-null when every member shares these coefficients
+    void *mailbox;
+    unsigned seq0;
+    double dt;
+};
+int resident_2d_query(int order, const Resident2D &r, bool *fits, size_t *mailbox_bytes);
+int launch_rk4_resident_2d(int order, const Resident2D &r, const CrossWeights &w, cudaStream_t stream);
 // Planar (re-plane / im-plane) working copy of psi used by the whole-grid time loop: lets the fused
 // kernel fetch its frames with TMA (cp.async.bulk.tensor, out-of-bounds zero fill = the truncated
 // stencil boundary).  Layout: psi planes [batch][2][rows][pitch], c12*P [batch][rows][pitch], pitch even.

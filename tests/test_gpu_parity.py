@@ -147,7 +147,7 @@ def test_runge_kutta_with_caller_supplied_band(nls):
     assert rel_l2(got, want) <= 1e-10
 
 
-@pytest.fixture(params=["tma32", "tma64", "tma32_persistent", "fused32", "fused64", "stream", "staged"])
+@pytest.fixture(params=["tma32", "tma64", "tma32_persistent", "fused32", "fused64", "stream", "resident", "staged"])
 def path_2d(request):
     """Both 2D implementations (fused whole-step kernel, per-stage kernels) are held to the same bar."""
     from nls_b200.engine import set_2d_path
@@ -199,6 +199,46 @@ def test_stream_kernel_is_bitwise_equal_to_tile_kernel(nls, order, n, iters):
         set_2d_path("auto")
     assert np.array_equal(a, b)
     assert rel_l2(a, O.dp.solve_nls_2d(*args)) <= 1e-10
+
+
+@pytest.mark.parametrize("order,n,iters", [(5, 512, 40), (5, 400, 25), (3, 300, 30), (7, 260, 20), (5, 131, 60), (5, 16, 50)])
+def test_resident_kernel_is_bitwise_equal_to_tile_kernel(nls, order, n, iters):
+    """The register-resident kernel (one patch per CTA, edge nodes exchanged through L2 mailboxes every RK stage)
+    performs each node's arithmetic in the order of the tile kernel: identical bits after `iters` steps."""
+    from nls_b200.engine import set_2d_path
+    m = model_2d(n, iters, order=order)
+    rng = np.random.default_rng(n)
+    P = m.getPumping() * (1.0 + 0.5 * rng.random((n, n)))
+    args = (m.dt, m.dx, order, iters, P, m.getCoefficients(), rough_field((n, n), n + 1) * 0.05 + 0.1)
+    try:
+        set_2d_path("resident")
+        a = nls.solve_nls_2d(*args)
+        set_2d_path("fused32")
+        b = nls.solve_nls_2d(*args)
+    finally:
+        set_2d_path("auto")
+    assert np.array_equal(a, b)
+
+
+def test_resident_kernel_batch_with_member_coefficients(nls):
+    from nls_b200.engine import Grid2D, set_2d_path
+    from nls_b200.model import dimensionless_coefficients
+    n, iters = 96, 40
+    ms = [model_2d(n, iters, radius=r) for r in (1.0, 2.0, 2.4)]
+    P = np.array([m.getPumping() for m in ms])
+    c = np.array([dimensionless_coefficients(dict(ORIG, gamma_R=g)) for g in (0.1, 0.242057488654, 0.7)])
+    out = {}
+    try:
+        for path in ("resident", "fused32"):
+            set_2d_path(path)
+            grid = Grid2D(n, 0.1, 1e-3, order=5, batch=3, pumping=P, coeffs=c, u0=0.1)
+            out[path] = grid.advance(iters // 2).advance(iters - iters // 2).solution()
+    finally:
+        set_2d_path("auto")
+    assert np.array_equal(out["resident"], out["fused32"])
+    for b, m in enumerate(ms):
+        want = O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, P[b], c[b], m.getInitialSolution())
+        assert rel_l2(out["resident"][b], want) <= 1e-10
 
 
 def test_stream_kernel_batch_with_member_coefficients(nls):
