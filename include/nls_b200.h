@@ -157,12 +157,14 @@ int nlsb_dev_band_matvec_1d(int n, int order, const double *taps, const double *
  * kernel read them from its constant bank), else NULL.
  * workspace: device scratch of nlsb_dev_rk4_2d_workspace() bytes. */
 size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols);
-/* Which kernels advance 2D grids: 0 = automatic (fused whole-step kernel, 32x32 tiles, TMA fill from a
- * planar working copy), 1 = one launch per RK stage, 2 / 3 = fused with 32x32 / 32x64 tiles filled by
- * plain loads, 4 / 5 = fused with 32x32 / 32x64 tiles filled by TMA, 6 / 7 = as 4 / 5 but the whole time
- * loop in one persistent launch when every tile is resident at once (experimental, slower).  All
- * give the same result to rounding (the fused variants bitwise); the switch exists for tests and
- * profiling. */
+/* Which kernels advance 2D grids: 0 = automatic (one launch per RK step: the strip-marching kernel for
+ * launches of >= 2^20 nodes, else the tile kernel with 32x32 tiles filled by TMA from a planar working
+ * copy), 1 = one launch per RK stage, 2 / 3 = tile kernel with 32x32 / 32x64 tiles filled by plain
+ * loads, 4 / 5 = tile kernel with 32x32 / 32x64 tiles filled by TMA, 6 / 7 = as 4 / 5 but the whole time
+ * loop in one persistent launch when every tile is resident at once (experimental, slower), 8 = the
+ * strip-marching kernel whatever the size, 9 = register-resident kernel, whole time loop in one launch
+ * with per-stage edge exchange through L2 (experimental, slower; falls back to 4 when the grid does not
+ * fit).  All give the same result to rounding (2..9 bitwise); the switch exists for tests and profiling. */
 int nlsb_set_2d_path(int path);
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
                     const double *wy, const double *pumping, const double *coeffs,
@@ -198,6 +200,30 @@ int nlsb_dev_cross_matvec_2d(int rows, int cols, int order, const double *wx, co
 /* r = c12 P / (c13 + c14 u_sqr) on npts points (coeffs on the HOST). */
 int nlsb_dev_reservoir(size_t npts, const double *coeffs_host, const double *pumping, const double *u_sqr,
                        double *r, nlsb_stream_t stream);
+
+/* Scalar diagnostics of device-resident states, one pass per member, nothing copied back but 8 doubles per
+ * member.  Replaces, for a state that lives on the device, what the reference computes on the host from the
+ * returned field: chemical_potential_1d/_2d (nls.f90:921-971; mu = i E / M with the MODEL's stencil order --
+ * the reference hard-wires 5), Solution.getDampingIntegral / getDensity / getReservoir (nls/model.py:350-380).
+ * out8: DEVICE, [batch][8] = {Re M, Im M, Re E, Im E, damping integral, particle number, max |psi|^2,
+ * max reservoir}, M = sum w conj(u) u, E = sum w conj(u) H(u), w = i*dx (1D) or 1 (2D); area element 2 pi r dx
+ * with r = linspace(0, n dx, n) (1D) or dx^2 (2D).  scratch: DEVICE, nlsb_dev_diagnostics_scratch(batch) bytes.
+ * Fixed reduction tree: results are reproducible run to run. */
+size_t nlsb_dev_diagnostics_scratch(int batch);
+int nlsb_dev_diagnostics_1d(int batch, int n, int order, double dx, const double *taps, const double *pumping,
+                            const double *coeffs, const double *psi, void *scratch, double *out8,
+                            nlsb_stream_t stream);
+int nlsb_dev_diagnostics_2d(int batch, int rows, int cols, int order, double dx, const double *wx,
+                            const double *wy, const double *pumping, const double *coeffs, const double *psi,
+                            void *scratch, double *out8, nlsb_stream_t stream);
+
+/* Pumping profiles of an ensemble generated on the device, sampled on the reference's grid (nls/model.py:220-232:
+ * dim 1: x = linspace(0, n dx, n); dim 2: x = y = linspace(-n dx/2, n dx/2, n), out[b][i][j] = P(x_j, y_i)).
+ * kind 0: GaussianPumping[1D|2D], kind 1: GaussianRingPumping[1D|2D] (nls/pumping.py:113-178).
+ * params_host: HOST [batch][5] = {power, x0, y0, variation, radius}; out: DEVICE [batch][n] or [batch][n][n].
+ * Grid and arithmetic are bit-identical to numpy's, exp() may differ in the last place (<= 4 ulp in the result). */
+int nlsb_dev_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_host,
+                              double *out, nlsb_stream_t stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnls_b200.so")
 
-SOURCES = ["api.cu", "kernels_1d.cu", "kernels_2d.cu", "fused_2d.cu", "stream_2d.cu", "resident_2d.cu", "reduce.cu", "operators.cpp"]
+SOURCES = ["api.cu", "kernels_1d.cu", "kernels_2d.cu", "fused_2d.cu", "stream_2d.cu", "resident_2d.cu", "reduce.cu", "diagnostics.cu", "pumping_gen.cu", "operators.cpp"]
 HEADERS = ["internal.h", "kernels.h", "device_math.cuh", "stream_2d_core.cuh", "resident_2d_core.cuh", os.path.join("..", "..", "include", "nls_b200.h")]
 
 NVCC_FLAGS = [

@@ -267,7 +267,8 @@ int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, d
 
     auto steps = [&](int first, int count, cudaStream_t s, int *rc) {
         for (int i = 0; i < count; ++i) {
-            int r = launch_rk4_step_fused_2d_planar(order, variant, p, maps, ((first + i) & 1) == 0, w, s);
+            // the first step follows the split kernel, which writes c12*P: no early start for that one
+            int r = launch_rk4_step_fused_2d_planar(order, variant, p, maps, ((first + i) & 1) == 0, first + i > 0, w, s);
             if (r && !*rc) *rc = r;
         }
     };
@@ -893,7 +894,7 @@ int nlsb_dev_rk4_step_2d_slab_planar(int rows_alloc, int cols, int order, double
     p.coeffs = nullptr; p.uniform = &shared; p.dt = dt;
     PlanarMaps maps;
     NLSB_TRY(make_planar_maps(order, variant, p, &maps));
-    NLSB_TRY(launch_rk4_step_fused_2d_planar(order, variant, p, maps, true, w, static_cast<cudaStream_t>(stream)));
+    NLSB_TRY(launch_rk4_step_fused_2d_planar(order, variant, p, maps, true, false, w, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 
@@ -918,6 +919,48 @@ int nlsb_dev_cross_matvec_2d(int rows, int cols, int order, const double *wx, co
     CrossWeights w{};
     NLSB_TRY(weights_from_host(order, wx, wy, &w));
     NLSB_TRY(launch_cross_matvec_2d(rows, cols, order, w, x, y, sign, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_host, double *out,
+                              nlsb_stream_t stream)
+{
+    if (!params_host || !out || batch < 1 || n < 1 || (dim != 1 && dim != 2) || (kind != 0 && kind != 1) || !(dx > 0.0))
+        return fail(NLSB_EINVAL, "dev_pumping_profiles: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Arena mem(s);
+    double *d_params;
+    NLSB_TRY(mem.upload(&d_params, params_host, (size_t)5 * batch));
+    NLSB_TRY(launch_pumping_profiles(dim, kind, batch, n, dx, d_params, out, s));
+    // the parameter table is pageable host memory: the copy above must have left it before we return
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+size_t nlsb_dev_diagnostics_scratch(int batch) { return batch > 0 ? diagnostics_scratch_bytes(batch) : 0; }
+
+int nlsb_dev_diagnostics_1d(int batch, int n, int order, double dx, const double *taps, const double *pumping,
+                            const double *coeffs, const double *psi, void *scratch, double *out8, nlsb_stream_t stream)
+{
+    if (!taps || !pumping || !coeffs || !psi || !scratch || !out8 || batch < 1 || !(dx > 0.0))
+        return fail(NLSB_EINVAL, "dev_diagnostics_1d: bad arguments");
+    NLSB_TRY(check_order_size(n, order));
+    NLSB_TRY(launch_diagnostics_1d(batch, n, order, dx, taps, pumping, coeffs, reinterpret_cast<const double2 *>(psi),
+                                   scratch, out8, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_diagnostics_2d(int batch, int rows, int cols, int order, double dx, const double *wx, const double *wy,
+                            const double *pumping, const double *coeffs, const double *psi, void *scratch, double *out8,
+                            nlsb_stream_t stream)
+{
+    if (!pumping || !coeffs || !psi || !scratch || !out8 || batch < 1 || !(dx > 0.0))
+        return fail(NLSB_EINVAL, "dev_diagnostics_2d: bad arguments");
+    NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    NLSB_TRY(launch_diagnostics_2d(batch, rows, cols, order, dx, w, pumping, coeffs, reinterpret_cast<const double2 *>(psi),
+                                   scratch, out8, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

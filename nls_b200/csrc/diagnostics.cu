@@ -1,0 +1,252 @@
+// diagnostics.cu -- the scalar diagnostics of a device-resident state in ONE pass per member.
+//
+// What the reference computes on the host after copying the field back:
+//   * chemical potential  mu = i <u, H u> / <u, u>   (chemical_potential_1d/_2d, nls.f90:921-971; weight r = i dx in
+//     the radial case, 1 on the square; the stencil order is the model's here, the reference hard-wires 5)
+//   * damping integral    sum (n - 1) |u|^2 dA        (Solution.getDampingIntegral, nls/model.py:350-365; dA = dx^2 on
+//     the square, 2 pi r dx with r = linspace(0, n dx, n) in the radial case)
+//   * particle number     sum |u|^2 dA,  peak density max |u|^2,  peak reservoir max n   (getDensity / getReservoir,
+//     nls/model.py:367-380)
+// The kernels evaluate v = H(u) on the fly (nothing is materialised), reduce with warp shuffles and a fixed
+// shared-memory tree, write one partial per CTA and finish per member in a second launch: the summation tree
+// depends only on (n, grid), so the numbers are run-to-run reproducible.
+//
+// Output per member: 8 doubles {Re M, Im M, Re E, Im E, damping, particles, max |u|^2, max reservoir} with
+// M = sum w conj(u) u, E = sum w conj(u) v; mu = i E / M.
+
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace nlsb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSums = 6;
+
+struct Acc {
+    double s[kSums];     // M_re, M_im, E_re, E_im, damping, particles
+    double m[2];         // max |u|^2, max reservoir
+};
+
+__device__ __forceinline__ Acc acc_zero()
+{
+    Acc a;
+#pragma unroll
+    for (int i = 0; i < kSums; ++i) a.s[i] = 0.0;
+    a.m[0] = a.m[1] = 0.0;
+    return a;
+}
+
+__device__ __forceinline__ Acc warp_reduce(Acc a)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < kSums; ++i) a.s[i] += __shfl_down_sync(0xffffffffu, a.s[i], off);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a.m[i] = fmax(a.m[i], __shfl_down_sync(0xffffffffu, a.m[i], off));
+    }
+    return a;
+}
+
+__device__ __forceinline__ Acc block_reduce(Acc a)
+{
+    __shared__ Acc part[kThreads / 32];
+    a = warp_reduce(a);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) part[warp] = a;
+    __syncthreads();
+    Acc t = acc_zero();
+    if (warp == 0) {
+        if (lane < kThreads / 32) t = part[lane];
+        t = warp_reduce(t);
+    }
+    return t;   // valid in thread 0
+}
+
+// One node's contribution: u the field, v = H(u), w the weight of the dot products, wd the area element.
+__device__ __forceinline__ void accumulate(Acc &a, const RhsCoeffs &c, double cp, double2 u, double2 v, double w, double wd)
+{
+    const double ur = u.x * w, ui = u.y * w, vr = v.x * w, vi = v.y * w;     // conj(u) * (x * w), as reduce.cu
+    a.s[0] += u.x * ur + u.y * ui;
+    a.s[1] += u.x * ui - u.y * ur;
+    a.s[2] += u.x * vr + u.y * vi;
+    a.s[3] += u.x * vi - u.y * vr;
+    const double usq = u.x * u.x + u.y * u.y;
+    const double res = cp / (c.c13 + c.c14 * usq);                             // getReservoir, nls/model.py:376-380
+    a.s[4] += (res - 1.0) * usq * wd;
+    a.s[5] += usq * wd;
+    a.m[0] = fmax(a.m[0], usq);
+    a.m[1] = fmax(a.m[1], res);
+}
+
+template <int K>
+struct WeightsK {
+    double wx[2 * K + 1];
+    double wy[2 * K + 1];
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+diagnostics_2d_kernel(int rows, int cols, double area, WeightsK<K> w, const double *__restrict__ pumping,
+                      const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial)
+{
+    const size_t member = blockIdx.y;
+    const size_t plane = (size_t)rows * cols;
+    const double2 *src = u + member * plane;
+    const double *P = pumping + member * plane;
+    const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
+    Acc a = acc_zero();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < plane; t += stride) {
+        const int y = (int)(t / cols), x = (int)(t % cols);
+        const double2 centre = src[t];
+        double lr = w.wx[K] * centre.x, li = w.wx[K] * centre.y;       // same tap order as stage_2d_kernel
+#pragma unroll
+        for (int s = 1; s <= K; ++s) {
+            if (x - s >= 0) {
+                const double2 v = src[t - s];
+                lr = fma(w.wx[K - s], v.x, lr);
+                li = fma(w.wx[K - s], v.y, li);
+            }
+            if (x + s < cols) {
+                const double2 v = src[t + s];
+                lr = fma(w.wx[K + s], v.x, lr);
+                li = fma(w.wx[K + s], v.y, li);
+            }
+            if (y - s >= 0) {
+                const double2 v = src[t - (size_t)s * cols];
+                lr = fma(w.wy[K - s], v.x, lr);
+                li = fma(w.wy[K - s], v.y, li);
+            }
+            if (y + s < rows) {
+                const double2 v = src[t + (size_t)s * cols];
+                lr = fma(w.wy[K + s], v.x, lr);
+                li = fma(w.wy[K + s], v.y, li);
+            }
+        }
+        const double cp = c.c12 * P[t];
+        accumulate(a, c, cp, centre, rhs_point(c, cp, centre, lr, li), 1.0, area);
+    }
+    a = block_reduce(a);
+    if (threadIdx.x == 0) partial[member * gridDim.x + blockIdx.x] = a;
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads)
+diagnostics_1d_kernel(int n, double dx, const double *__restrict__ taps, const double *__restrict__ pumping,
+                      const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial)
+{
+    constexpr int K = (M - 1) / 2;
+    const size_t member = blockIdx.y;
+    const double2 *um = u + member * n;
+    const double *P = pumping + member * n;
+    const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
+    const double ring = n > 1 ? (n * dx) / (n - 1) : 0.0;              // spacing of linspace(0, n dx, n)
+    Acc a = acc_zero();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double lr = 0.0, li = 0.0;
+#pragma unroll
+        for (int t = 0; t < M; ++t) {
+            const int j = i + t - K;
+            if (j >= 0 && j < n) {
+                const double tap = taps[(size_t)i * M + t];
+                lr = fma(tap, um[j].x, lr);
+                li = fma(tap, um[j].y, li);
+            }
+        }
+        const double cp = c.c12 * P[i];
+        const double w = ((double)(i + 1) - 1.0) * dx;                  // chemical_potential_1d, nls.f90:940-947
+        const double wd = 6.283185307179586 * (i * ring) * dx;          // getDampingIntegral, nls/model.py:357-361
+        accumulate(a, c, cp, um[i], rhs_point(c, cp, um[i], lr, li), w, wd);
+    }
+    a = block_reduce(a);
+    if (threadIdx.x == 0) partial[member * gridDim.x + blockIdx.x] = a;
+}
+
+__global__ void __launch_bounds__(kThreads)
+finish_diagnostics_kernel(int nparts, const Acc *__restrict__ partial, double *__restrict__ out8)
+{
+    const size_t member = blockIdx.x;
+    Acc a = acc_zero();
+    for (int t = threadIdx.x; t < nparts; t += blockDim.x) {
+        const Acc p = partial[member * nparts + t];
+#pragma unroll
+        for (int i = 0; i < kSums; ++i) a.s[i] += p.s[i];
+        a.m[0] = fmax(a.m[0], p.m[0]);
+        a.m[1] = fmax(a.m[1], p.m[1]);
+    }
+    a = block_reduce(a);
+    if (threadIdx.x == 0) {
+        double *o = out8 + member * 8;
+#pragma unroll
+        for (int i = 0; i < kSums; ++i) o[i] = a.s[i];
+        o[6] = a.m[0];
+        o[7] = a.m[1];
+    }
+}
+
+int parts_for(size_t npts, int batch)
+{
+    size_t blocks = (npts + kThreads - 1) / kThreads;
+    // enough CTAs to fill the GPU across the batch, at most 592 partials per member
+    size_t cap = batch >= 148 ? 8 : 592 / (size_t)batch + 1;
+    if (cap > 592) cap = 592;
+    if (blocks > cap) blocks = cap;
+    return blocks ? (int)blocks : 1;
+}
+
+template <int K>
+WeightsK<K> pack(const CrossWeights &w)
+{
+    WeightsK<K> p;
+    for (int t = 0; t < 2 * K + 1; ++t) {
+        p.wx[t] = w.wx[t];
+        p.wy[t] = w.wy[t];
+    }
+    return p;
+}
+
+}  // namespace
+
+size_t diagnostics_scratch_bytes(int batch) { return sizeof(Acc) * 592 * (size_t)(batch > 0 ? batch : 1); }
+
+int launch_diagnostics_2d(int batch, int rows, int cols, int order, double dx, const CrossWeights &w,
+                          const double *pumping, const double *coeffs, const double2 *u, void *scratch, double *out8,
+                          cudaStream_t stream)
+{
+    if (batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", batch);
+    const int parts = parts_for((size_t)rows * cols, batch);
+    const dim3 grid((unsigned)parts, (unsigned)batch);
+    Acc *partial = static_cast<Acc *>(scratch);
+    switch (order) {
+    case 3: diagnostics_2d_kernel<1><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<1>(w), pumping, coeffs, u, partial); break;
+    case 5: diagnostics_2d_kernel<2><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<2>(w), pumping, coeffs, u, partial); break;
+    case 7: diagnostics_2d_kernel<3><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<3>(w), pumping, coeffs, u, partial); break;
+    default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+    }
+    finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, partial, out8);
+    count_launches(2);
+    return (int)cudaGetLastError();
+}
+
+int launch_diagnostics_1d(int batch, int n, int order, double dx, const double *taps, const double *pumping,
+                          const double *coeffs, const double2 *u, void *scratch, double *out8, cudaStream_t stream)
+{
+    if (batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", batch);
+    const int parts = parts_for((size_t)n, batch);
+    const dim3 grid((unsigned)parts, (unsigned)batch);
+    Acc *partial = static_cast<Acc *>(scratch);
+    switch (order) {
+    case 3: diagnostics_1d_kernel<3><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;
+    case 5: diagnostics_1d_kernel<5><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;
+    case 7: diagnostics_1d_kernel<7><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;
+    default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+    }
+    finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, partial, out8);
+    count_launches(2);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace nlsb

@@ -421,15 +421,21 @@ rk4_step_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant
     if (TMA) {
         // ---- fill by TMA: three boxes (re frame, im frame, c12*P); elements outside the arrays arrive
         // as zeros, which is exactly the truncated (zero outside the square) stencil boundary ----
+        // Programmatic dependent launch: the next step's grid may start (and run this prologue, including the
+        // fetch of c12*P, which no step writes) while this grid is still running; psi is requested only after
+        // griddepcontrol.wait, i.e. once the previous step has completed and its stores are visible.  Every
+        // global store of this grid comes after the psi frame has arrived, hence after that wait too.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         const uint32_t bar = smem_u32(smem_raw + 2 * C::PLANE0 + 5 * C::PLANE1);
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0) {
             constexpr uint32_t bytes = sizeof(double) * (2 * C::W0 * C::H0 + C::W1 * C::H1);
             mbar_expect_tx(bar, bytes);
+            tma_load_3d(smem_u32(sm.cp()), &map_cp, bar, t.x0 + C::OX, t.y0 + C::OY, (int)member);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             tma_load_3d(smem_u32(sm.re0()), &map_in, bar, t.x0, t.y0, (int)(2 * member));
             tma_load_3d(smem_u32(sm.im0()), &map_in, bar, t.x0, t.y0, (int)(2 * member + 1));
-            tma_load_3d(smem_u32(sm.cp()), &map_cp, bar, t.x0 + C::OX, t.y0 + C::OY, (int)member);
         }
         mbar_wait(bar, 0);
     } else {
@@ -662,7 +668,7 @@ int launch_fused_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t s
 }
 
 template <typename C, bool UNIFORM>
-int launch_fused_planar_cfg(const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b, const CrossWeights &w,
+int launch_fused_planar_cfg(const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b, bool overlap, const CrossWeights &w,
                             cudaStream_t stream)
 {
     int rc = configure_fused<C, UNIFORM, true>();
@@ -682,9 +688,22 @@ int launch_fused_planar_cfg(const Fused2DPlanar &p, const PlanarMaps &maps, bool
     std::memcpy(in.bytes, a_to_b ? maps.psi_a : maps.psi_b, 128);
     std::memcpy(cp.bytes, maps.cp, 128);
     const dim3 grid((unsigned)(a.tiles_x * a.tiles_y), (unsigned)p.batch);
-    rk4_step_fused_kernel<C, UNIFORM, true><<<grid, C::THREADS, C::SMEM, stream>>>(a, pack_weights<C>(w), in, cp);
+    // programmatic stream serialization: this grid may begin before the previous one in the stream has drained
+    // (the kernel orders its own reads and writes with griddepcontrol.wait)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = overlap ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const WeightsArg<C::K> wa = pack_weights<C>(w);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rk4_step_fused_kernel<C, UNIFORM, true>, a, wa, in, cp);
     count_launches(1);
-    return (int)cudaGetLastError();
+    return (int)e;
 }
 
 template <typename C, bool UNIFORM>
@@ -756,16 +775,16 @@ int launch_fused_k(int variant, const Fused2DStep &s, const CrossWeights &w, cud
 }
 
 template <int K>
-int launch_fused_planar_k(int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
+int launch_fused_planar_k(int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b, bool overlap,
                           const CrossWeights &w, cudaStream_t stream)
 {
     using Small = typename Shapes<K>::Small;
     using Tall = typename Shapes<K>::Tall;
     if (K == 3 || variant == 0)
-        return p.uniform ? launch_fused_planar_cfg<Small, true>(p, maps, a_to_b, w, stream)
-                         : launch_fused_planar_cfg<Small, false>(p, maps, a_to_b, w, stream);
-    return p.uniform ? launch_fused_planar_cfg<Tall, true>(p, maps, a_to_b, w, stream)
-                     : launch_fused_planar_cfg<Tall, false>(p, maps, a_to_b, w, stream);
+        return p.uniform ? launch_fused_planar_cfg<Small, true>(p, maps, a_to_b, overlap, w, stream)
+                         : launch_fused_planar_cfg<Small, false>(p, maps, a_to_b, overlap, w, stream);
+    return p.uniform ? launch_fused_planar_cfg<Tall, true>(p, maps, a_to_b, overlap, w, stream)
+                     : launch_fused_planar_cfg<Tall, false>(p, maps, a_to_b, overlap, w, stream);
 }
 
 template <int K>
@@ -926,13 +945,13 @@ int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const
 }
 
 int launch_rk4_step_fused_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
-                                    const CrossWeights &w, cudaStream_t stream)
+                                    bool overlap, const CrossWeights &w, cudaStream_t stream)
 {
     if (p.batch > 32767) return fail(NLSB_ESIZE, "batch = %d exceeds the planar-path limit 32767", p.batch);
     switch (order) {
-    case 3: return launch_fused_planar_k<1>(variant, p, maps, a_to_b, w, stream);
-    case 5: return launch_fused_planar_k<2>(variant, p, maps, a_to_b, w, stream);
-    case 7: return launch_fused_planar_k<3>(variant, p, maps, a_to_b, w, stream);
+    case 3: return launch_fused_planar_k<1>(variant, p, maps, a_to_b, overlap, w, stream);
+    case 5: return launch_fused_planar_k<2>(variant, p, maps, a_to_b, overlap, w, stream);
+    case 7: return launch_fused_planar_k<3>(variant, p, maps, a_to_b, overlap, w, stream);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
 }

@@ -97,9 +97,11 @@ int make_planar_maps(int order, int variant, const Fused2DPlanar &p, PlanarMaps 
 // psi (interleaved) -> planes of buffer A, and c12*P; buffer A/B -> psi (interleaved)
 int launch_split_planar(const Fused2DPlanar &p, const double2 *psi, const double *pumping, cudaStream_t stream);
 int launch_join_planar(const Fused2DPlanar &p, bool from_b, double2 *psi, cudaStream_t stream);
-// one RK4 step A -> B (a_to_b) or B -> A
+// one RK4 step A -> B (a_to_b) or B -> A.  overlap: the launch may begin before the previous kernel of the stream
+// has drained (programmatic dependent launch; the kernel waits for it before touching psi) -- only valid when
+// that previous kernel is the preceding step of the same time loop (c12*P is read before the wait).
 int launch_rk4_step_fused_2d_planar(int order, int variant, const Fused2DPlanar &p, const PlanarMaps &maps, bool a_to_b,
-                                    const CrossWeights &w, cudaStream_t stream);
+                                    bool overlap, const CrossWeights &w, cudaStream_t stream);
 // Persistent variant: `steps` RK4 steps (A -> B -> A ...) in ONE cooperative launch; usable when all tiles
 // are resident at once (persistent_2d_fits).  flags: zeroed device ints, one per tile.
 int persistent_2d_fits(int order, int variant, const Fused2DPlanar &p, bool *fits, long long *tiles);
@@ -107,6 +109,16 @@ int launch_rk4_persistent_2d_planar(int order, int variant, const Fused2DPlanar 
                                     int *flags, const CrossWeights &w, cudaStream_t stream);
 int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,
                            double sign, cudaStream_t stream);
+// diagnostics.cu: fused scalar diagnostics of device-resident states (8 doubles per member, see nls_b200.h)
+size_t diagnostics_scratch_bytes(int batch);
+int launch_diagnostics_2d(int batch, int rows, int cols, int order, double dx, const CrossWeights &w,
+                          const double *pumping, const double *coeffs, const double2 *u, void *scratch, double *out8,
+                          cudaStream_t stream);
+int launch_diagnostics_1d(int batch, int n, int order, double dx, const double *taps, const double *pumping,
+                          const double *coeffs, const double2 *u, void *scratch, double *out8, cudaStream_t stream);
+// pumping_gen.cu: profiles of an ensemble generated on the device; params_dev: [batch][5] on the device
+int launch_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_dev, double *out,
+                            cudaStream_t stream);
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,
                      cudaStream_t stream);
 

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["Ensemble1D", "Grid2D", "radial_taps", "cross_weights", "require_cuda"]
+__all__ = ["Ensemble1D", "Grid2D", "radial_taps", "cross_weights", "require_cuda", "device_pumping"]
 
 
 def require_cuda():
@@ -77,6 +77,37 @@ def _to_device(a, dtype, device):
     return torch.from_numpy(np.array(a, order="C", copy=True)).to(device=device, dtype=dtype)
 
 
+def device_pumping(dim, kind, n, dx, power, variation, radius=0.0, x0=0.0, y0=0.0, device=None):
+    """Pumping profiles of an ensemble sampled ON THE DEVICE on the reference's grid (``model.py:220-232``).
+
+    kind: "gaussian" (``GaussianPumping1D/2D``) or "ring" (``GaussianRingPumping1D/2D``); power, variation, radius,
+    x0, y0: scalars or arrays of one value per member (broadcast).  Returns a float64 tensor (batch, n) or
+    (batch, n, n) that ``Ensemble1D`` / ``Grid2D`` accept as ``pumping``.  Grid and arithmetic are bit-identical to
+    the host classes in ``nls_b200.pumping``; exp() may differ in the last place (C ABI nlsb_dev_pumping_profiles).
+    """
+    require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    cols = np.broadcast_arrays(*[np.atleast_1d(np.asarray(v, dtype=np.float64)) for v in (power, x0, y0, variation, radius)])
+    params = np.ascontiguousarray(np.stack(cols, axis=1))
+    batch = params.shape[0]
+    shape = (batch, int(n)) if int(dim) == 1 else (batch, int(n), int(n))
+    out = torch.empty(shape, dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        _lib.call("nlsb_dev_pumping_profiles", int(dim), {"gaussian": 0, "ring": 1}[kind], batch, int(n), float(dx),
+                  params.ctypes.data_as(C.c_void_p), _dptr(out), _stream())
+    return out
+
+
+def _diagnostics_dict(out8):
+    """Host view of the [batch][8] result of nlsb_dev_diagnostics_*: chemical potential mu = i E / M
+    (nls.f90:946-947, :968-970) and the other scalars, one entry per member."""
+    d = out8.cpu().numpy()
+    M = d[:, 0] + 1j * d[:, 1]
+    E = d[:, 2] + 1j * d[:, 3]
+    return {"chemical_potential": 1j * E / M, "damping_integral": d[:, 4].copy(), "particles": d[:, 5].copy(),
+            "max_density": d[:, 6].copy(), "max_reservoir": d[:, 7].copy()}
+
+
 class Ensemble1D(object):
     """``batch`` independent radial systems of ``n`` nodes sharing dx, dt and the stencil order.
 
@@ -119,6 +150,28 @@ class Ensemble1D(object):
             _lib.call("nlsb_dev_hamiltonian_1d", self.batch, self.n, self.order, _dptr(self.taps), _dptr(self.pumping),
                       _dptr(self.coeffs), _dptr(u), _dptr(v), _stream())
         return v
+
+    def diagnostics(self):
+        """Chemical potential, damping integral, particle number, peak density and peak reservoir of every member,
+        reduced on the device in one pass (only 8 doubles per member cross the bus); see nlsb_dev_diagnostics_1d."""
+        out = torch.empty((self.batch, 8), dtype=torch.float64, device=self.device)
+        scratch = torch.empty(_lib.load().nlsb_dev_diagnostics_scratch(self.batch), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("nlsb_dev_diagnostics_1d", self.batch, self.n, self.order, self.dx, _dptr(self.taps),
+                      _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi), _dptr(scratch), _dptr(out), _stream())
+        return _diagnostics_dict(out)
+
+    def set_pumping(self, pumping):
+        """Replace the pumping profile(s) between chunks of steps; psi and the tap table stay on the device
+        (the continuation pattern of nls/animation.py:64-101 and tools/check.py:34-36)."""
+        with torch.cuda.device(self.device):
+            self.pumping.copy_(self._field(pumping, torch.float64))
+        return self
+
+    def set_coefficients(self, coeffs):
+        with torch.cuda.device(self.device):
+            self.coeffs.copy_(_to_device(_coeff_table(coeffs, self.batch), torch.float64, self.device))
+        return self
 
     def solution(self):
         return self.psi.cpu().numpy()
@@ -177,6 +230,30 @@ class Grid2D(object):
             _lib.call("nlsb_dev_hamiltonian_2d", self.batch, self.rows, self.cols, self.order, self._w(self.wx),
                       self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), _dptr(u), _dptr(v), _stream())
         return v
+
+    def diagnostics(self):
+        """As ``Ensemble1D.diagnostics`` for 2D grids (area element dx^2, chemical potential weight 1)."""
+        out = torch.empty((self.batch, 8), dtype=torch.float64, device=self.device)
+        scratch = torch.empty(_lib.load().nlsb_dev_diagnostics_scratch(self.batch), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("nlsb_dev_diagnostics_2d", self.batch, self.rows, self.cols, self.order, self.dx,
+                      self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi),
+                      _dptr(scratch), _dptr(out), _stream())
+        return _diagnostics_dict(out)
+
+    def set_pumping(self, pumping):
+        """Replace the pumping profile(s) between chunks of steps; psi and the operator stay on the device
+        (the continuation pattern of nls/animation.py:64-101 and tools/check.py:34-36)."""
+        with torch.cuda.device(self.device):
+            self.pumping.copy_(self._field(pumping, torch.float64))
+        return self
+
+    def set_coefficients(self, coeffs):
+        table = _coeff_table(coeffs, self.batch)
+        self.shared_coeffs = table[0].copy() if bool((table == table[0]).all()) else None
+        with torch.cuda.device(self.device):
+            self.coeffs.copy_(_to_device(table, torch.float64, self.device))
+        return self
 
     def solution(self):
         return self.psi.cpu().numpy()

@@ -28,20 +28,22 @@ def main():
     from nls_b200.multigpu import SlabGrid2D, shard_range
     from test_gpu_parity import model_1d, model_2d, rel_l2, rough_field
 
-    n, iters = 512, 40
-    m = model_2d(n, iters)
-    u0 = 0.1 + 0.05 * rough_field((n, n), 5)
-    slab = SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0)
-    full = slab.advance(iters).gather()
     ok = True
-    if rank == 0:
-        from oracle import oracle as O
-        single = Grid2D(n, m.dx, m.dt, order=5, pumping=m.getPumping(), coeffs=m.getCoefficients(), u0=u0)
-        single = single.advance(iters).solution()[0]
-        bitwise = bool(np.array_equal(full, single))
-        err = rel_l2(full, O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), m.getCoefficients(), u0))
-        print("slabs over %d ranks: bitwise equal to 1 GPU: %s, rel-L2 vs oracle %.2e" % (world, bitwise, err))
-        ok = bitwise and err <= 1e-10
+    # 512: planar slabs + TMA tile kernel; 2048: interleaved slabs + strip-marching kernel (>= 2^20 owned nodes)
+    for n, iters in ((512, 40), (2048, 6)):
+        m = model_2d(n, iters, radius=min(10.0, n * 0.1 / 4))
+        u0 = 0.1 + 0.05 * rough_field((n, n), 5)
+        slab = SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0)
+        full = slab.advance(iters).gather()
+        if rank == 0:
+            from oracle import oracle as O
+            single = Grid2D(n, m.dx, m.dt, order=5, pumping=m.getPumping(), coeffs=m.getCoefficients(), u0=u0)
+            single = single.advance(iters).solution()[0]
+            bitwise = bool(np.array_equal(full, single))
+            err = rel_l2(full, O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), m.getCoefficients(), u0))
+            print("slabs %d^2 over %d ranks (%s layout): bitwise equal to 1 GPU: %s, rel-L2 vs oracle %.2e"
+                  % (n, world, "planar" if slab.planar else "interleaved", bitwise, err))
+            ok = ok and bitwise and err <= 1e-10
 
     # ensemble sharding: each rank advances its members; results gathered and compared with one launch
     B, n1 = 16, 400

@@ -107,3 +107,122 @@ def test_hamiltonian_device_api():
     blocks, orders = O.dp.make_laplacian_2d(80, 5, m2.dx)
     want2 = O.dp.hamiltonian_2d(m2.getPumping(), m2.getCoefficients(), u2, blocks, orders)
     assert rel_l2(g.hamiltonian().cpu().numpy()[0], want2) <= 1e-13
+
+
+def _host_diagnostics(m, u, order, dim):
+    """The reference's own host-side formulas (model.py mirror) + the oracle's chemical potential."""
+    from nls_b200.model import Solution
+    sol = Solution(m, u)
+    P, c = m.getPumping(), m.getCoefficients()
+    if dim == 1:
+        op = O.dp.make_laplacian(u.shape[0], order, m.dx)
+        v = O.dp.hamiltonian(P, c, u, op)
+        w = np.arange(u.shape[0]) * m.dx
+    else:
+        blocks, orders = O.dp.make_laplacian_2d(u.shape[0], order, m.dx)
+        v = O.dp.hamiltonian_2d(P, c, u, blocks, orders)
+        w = 1.0
+    mu = 1j * np.sum(w * np.conj(u) * v) / np.sum(w * np.conj(u) * u)
+    dens = sol.getDensity()
+    if dim == 1:
+        r = np.linspace(0, u.shape[0] * m.dx, u.shape[0])
+        particles = 2 * np.pi * np.sum(dens * r * m.dx)
+    else:
+        particles = np.sum(dens) * m.dx ** 2
+    return mu, sol.getDampingIntegral(), particles, dens.max(), sol.getReservoir().max()
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+def test_device_diagnostics_match_host_formulas(order):
+    """chemical potential, damping integral, particle number, peak density / reservoir reduced on
+    the device against the reference's host formulas (nls/model.py:350-380) and the oracle's H(u); 1e-12."""
+    from nls_b200.engine import Ensemble1D, Grid2D
+    m1 = model_1d(400, order=order)
+    u1 = np.array([rough_field(400, s) * 0.3 + 0.2 for s in (1, 2, 3)])
+    P1 = np.array([m1.getPumping() * f for f in (0.5, 1.0, 2.0)])
+    e = Ensemble1D(400, m1.dx, m1.dt, order=order, batch=3, pumping=P1, coeffs=m1.getCoefficients(), u0=u1)
+    d = e.diagnostics()
+    for b in range(3):
+        m1.setPumping(lambda *grid, profile=P1[b]: profile)     # the model samples a functor
+        mu, damp, part, dmax, rmax = _host_diagnostics(m1, u1[b], order, 1)
+        got = (d["chemical_potential"][b], d["damping_integral"][b], d["particles"][b], d["max_density"][b], d["max_reservoir"][b])
+        for g, w_ in zip(got, (mu, damp, part, dmax, rmax)):
+            assert abs(g - w_) <= 1e-12 * max(abs(w_), 1.0), (order, b, g, w_)
+    n = 96
+    m2 = model_2d(n, order=order, radius=2.0)
+    u2 = np.array([rough_field((n, n), s) * 0.3 + 0.2 for s in (4, 5)])
+    g2 = Grid2D(n, m2.dx, m2.dt, order=order, batch=2, pumping=m2.getPumping(), coeffs=m2.getCoefficients(), u0=u2)
+    d = g2.diagnostics()
+    for b in range(2):
+        mu, damp, part, dmax, rmax = _host_diagnostics(m2, u2[b], order, 2)
+        got = (d["chemical_potential"][b], d["damping_integral"][b], d["particles"][b], d["max_density"][b], d["max_reservoir"][b])
+        for g, w_ in zip(got, (mu, damp, part, dmax, rmax)):
+            assert abs(g - w_) <= 1e-12 * max(abs(w_), 1.0), (order, b, g, w_)
+    # the reference's entry point (order 5 hard-wired) agrees with the device path
+    if order == 5:
+        from nls_b200.native import nls
+        assert abs(nls.chemical_potential_2d(m2.dx, m2.getPumping(), m2.getCoefficients(), u2[0]) - d["chemical_potential"][0].real) <= 1e-12
+    again = g2.diagnostics()
+    assert all(np.array_equal(again[k], d[k]) for k in d)           # fixed reduction tree: reproducible
+
+
+def test_continuation_with_changing_pumping_equals_fresh_solves():
+    """psi stays on the device across chunks while the pump changes (animation / check loops)."""
+    from nls_b200.engine import Grid2D
+    n = 64
+    m = model_2d(n, radius=1.5)
+    P, c = m.getPumping(), m.getCoefficients()
+    grid = Grid2D(n, m.dx, m.dt, pumping=P, coeffs=c, u0=0.1)
+    grid.advance(50).set_pumping(0.5 * P).advance(30).set_pumping(P).advance(20)
+    u = O.dp.solve_nls_2d(m.dt, m.dx, 5, 50, P, c, 0.1 * np.ones((n, n), dtype=complex))
+    u = O.dp.solve_nls_2d(m.dt, m.dx, 5, 30, 0.5 * P, c, u)
+    u = O.dp.solve_nls_2d(m.dt, m.dx, 5, 20, P, c, u)
+    assert rel_l2(grid.solution()[0], u) <= 1e-10
+
+
+def _ulps(got, want):
+    return np.max(np.abs(got - want) / (np.spacing(np.abs(want)) + 1e-300))
+
+
+def test_device_pumping_profiles_match_host_classes_to_4_ulp():
+    """ensemble pumping profiles generated on the device against the host classes (bit-exact to
+    the reference's nls/pumping.py); policy: grid and arithmetic identical, exp() within the last place."""
+    from nls_b200.engine import device_pumping
+    from nls_b200.model import Problem
+    from nls_b200 import pumping as H
+    n1, n2, dx = 400, 96, 0.1
+    powers, radii, vars_ = np.array([1.0, 20.0, 37.5]), np.array([2.0, 10.0, 17.0]), np.array([3.14, 1.0, 5.0])
+    m1 = Problem().model(model="1d", dx=dx, dt=1e-3, u0=0.1, order=5, num_nodes=n1, num_iters=1, pumping=H.GaussianPumping1D())
+    m2 = Problem().model(model="2d", dx=dx, dt=1e-3, u0=0.1, order=5, num_nodes=n2, num_iters=1, pumping=H.GaussianPumping2D())
+    got = device_pumping(1, "ring", n1, dx, powers, vars_, radius=radii).cpu().numpy()
+    for b in range(3):
+        m1.setPumping(H.GaussianRingPumping1D(power=powers[b], radius=radii[b], variation=vars_[b]))
+        assert _ulps(got[b], m1.getPumping()) <= 4
+    got = device_pumping(1, "gaussian", n1, dx, powers, vars_, x0=radii).cpu().numpy()
+    for b in range(3):
+        m1.setPumping(H.GaussianPumping1D(power=powers[b], x0=radii[b], variation=vars_[b]))
+        assert _ulps(got[b], m1.getPumping()) <= 4
+    got = device_pumping(2, "ring", n2, dx, powers, vars_, radius=radii / 4, x0=0.3, y0=-0.2).cpu().numpy()
+    for b in range(3):
+        m2.setPumping(H.GaussianRingPumping2D(power=powers[b], x0=0.3, y0=-0.2, variation=vars_[b], radius=radii[b] / 4))
+        assert _ulps(got[b], m2.getPumping()) <= 4
+    got = device_pumping(2, "gaussian", n2, dx, powers, vars_, x0=0.3, y0=-0.2).cpu().numpy()
+    for b in range(3):
+        m2.setPumping(H.GaussianPumping2D(power=powers[b], x0=0.3, y0=-0.2, variation=vars_[b]))
+        assert _ulps(got[b], m2.getPumping()) <= 4
+
+
+def test_ensemble_from_device_generated_pumping():
+    """An ensemble whose profiles never exist on the host: members match solves fed with the host profiles (the
+    last-place differences of exp() stay far below the 1e-10 bar)."""
+    from nls_b200.engine import Grid2D, device_pumping
+    n, iters = 128, 60
+    radii = np.array([1.0, 2.0, 3.0, 4.0])
+    P = device_pumping(2, "ring", n, 0.1, 20.0, 3.14 / 4, radius=radii)
+    m = model_2d(n, iters)
+    grid = Grid2D(n, 0.1, 1e-3, batch=4, pumping=P, coeffs=m.getCoefficients(), u0=0.1).advance(iters)
+    from nls_b200.pumping import GaussianRingPumping2D
+    for b, r in enumerate(radii):
+        m.setPumping(GaussianRingPumping2D(power=20.0, radius=float(r), variation=3.14 / 4))
+        want = O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
+        assert rel_l2(grid.solution()[b], want) <= 1e-10
