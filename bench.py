@@ -242,6 +242,9 @@ def run_engine(args):
     if args.batch:
         batch = args.batch
     w = build_inputs(name, args.iters, batch, args.n)
+    if args.order:
+        w["order"] = args.order
+        w["desc"] += " [order overridden: %d]" % args.order
     if shard:
         lo, hi = rank * w["batch"] // world, (rank + 1) * w["batch"] // world
         for key in ("pumping", "coeffs", "u0"):
@@ -388,6 +391,7 @@ def main():
     ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
     ap.add_argument("--n", type=int, default=None, help="override the grid size (profiling only)")
+    ap.add_argument("--order", type=int, default=None, help="override the stencil order (profiling only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "resident", "staged"], default="auto", help="2D kernel family")
     args = ap.parse_args()

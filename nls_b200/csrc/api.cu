@@ -144,13 +144,15 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
 // 8 = streaming strip-marching kernel (stream_2d.cu) on interleaved psi, one launch per step,
 // 9 = resident kernel (resident_2d.cu): the whole time loop in one cooperative launch, field in registers,
 //     for grids whose patches are all resident at once (falls back to 4 otherwise).
-// Automatic: the streaming kernel for launches of at least 2^20 nodes (measured on B200: 1.0x the tile kernel at
-// 1024^2, 1.5x at 2048^2, 1.56x at 8192^2), the TMA tile kernel below that.  Both produce the same bits.
+// Automatic: the streaming kernel for launches of at least 2^20 nodes (measured on B200, order 5: 1.0x the tile
+// kernel at 1024^2, 1.5x at 2048^2, 1.56x at 8192^2; 4096^2: 1.75x at order 3, 1.84x at order 7), the TMA tile
+// kernel below that -- with 32x64 tiles when those give every SM at most one CTA while 32x32 tiles would not
+// (512^2: 7.86 vs 8.21 us per step), else 32x32.  All produce the same bits.
 static std::atomic<int> g_path_2d{0};
 
 static bool stream_preferred(int order, int batch, int out_rows, int cols)
 {
-    return (order == 3 || order == 5) && (cols & 1) == 0 && (long long)batch * out_rows * cols >= (1ll << 20);
+    return (cols & 1) == 0 && (long long)batch * out_rows * cols >= (1ll << 20);
 }
 
 static int launch_interleaved_step(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
@@ -351,8 +353,16 @@ int enqueue_rk4_2d(int batch, int rows, int cols, int order, int iters, double d
     if (path == 2 || path == 3 || path == 8 || batch > 32767 || rows > 65535 ||
         (path == 0 && stream_preferred(order, batch, rows, cols)))
         return enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, stream);
-    return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work,
-                                 (path == 5 || path == 7) ? 1 : 0, path == 6 || path == 7, stream);
+    int variant = (path == 5 || path == 7) ? 1 : 0;
+    if (path == 0 && order != 7) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long small = (long long)((cols + 31) / 32) * ((rows + 31) / 32) * batch;
+        const long long tall = (long long)((cols + 31) / 32) * ((rows + 63) / 64) * batch;
+        if (small > sms && tall <= sms) variant = 1;
+    }
+    return enqueue_rk4_2d_planar(batch, rows, cols, order, iters, dt, w, pumping, coeffs, psi, work, variant,
+                                 path == 6 || path == 7, stream);
 }
 
 int enqueue_rk4_2d_staged(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,

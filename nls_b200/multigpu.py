@@ -136,7 +136,7 @@ def _cuda_stepper_interleaved(plan, cols, dx, dt, order, coeffs):
 def _default_cuda_stepper(plan, cols, dx, dt, order, coeffs):
     # slabs large enough for the strip-marching kernel (api.cu: stream_preferred) use the interleaved layout
     lo, hi = plan.owned
-    if order in (3, 5) and cols % 2 == 0 and (hi - lo) * cols >= (1 << 20):
+    if cols % 2 == 0 and (hi - lo) * cols >= (1 << 20):
         return _cuda_stepper_interleaved(plan, cols, dx, dt, order, coeffs)
     return _cuda_stepper(plan, cols, dx, dt, order, coeffs)
 

@@ -226,3 +226,71 @@ def test_ensemble_from_device_generated_pumping():
         m.setPumping(GaussianRingPumping2D(power=20.0, radius=float(r), variation=3.14 / 4))
         want = O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), m.getCoefficients(), m.getInitialSolution())
         assert rel_l2(grid.solution()[b], want) <= 1e-10
+
+
+def test_sweep_front_end_single_gpu():
+    """a parameter scan as one ensemble launch; every point agrees with its own oracle solve."""
+    from nls_b200.sweep import run_sweep, SweepPoint
+    from nls_b200.model import Problem, Solution
+    from nls_b200.pumping import GaussianRingPumping2D
+    n, iters = 64, 80
+    points = [dict(power=p, radius=1.5, variation=0.8, gamma_R=g) for p in (5.0, 20.0) for g in (0.1, 0.242057488654, 0.6)]
+    table = run_sweep(points, model="2d", kind="ring", num_nodes=n, num_iters=iters, keep_fields=True)
+    assert table["solution"].shape == (6, n, n)
+    for i, pt in enumerate(points):
+        m = Problem().model(model="2d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=iters,
+                            pumping=GaussianRingPumping2D(power=pt["power"], radius=1.5, variation=0.8))
+        c = SweepPoint(pt).coefficients()
+        want = O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), c, m.getInitialSolution())
+        assert rel_l2(table["solution"][i], want) <= 1e-10
+        m.coeffs = c
+        assert abs(table["damping_integral"][i] - Solution(m, want).getDampingIntegral()) <= 1e-9 * abs(table["particles"][i])
+
+
+def test_c4_full_size_properties():
+    """8192 x 8192 ring pump (BASELINE config 4, strip-marching kernel), properties that need no oracle run:
+    mirror / transpose symmetry of the ring problem, U(1) covariance, continuation additivity (bitwise)."""
+    import torch
+    from nls_b200.engine import Grid2D, device_pumping
+    n = 8192
+    m = model_2d(64)
+    c = m.getCoefficients()
+    P = device_pumping(2, "ring", n, 0.1, 20.0, 50.0, radius=200.0)
+
+    def dev_rel(a, b):
+        return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+
+    base = Grid2D(n, 0.1, 1e-3, pumping=P, coeffs=c, u0=0.1).advance(3).psi[0].clone()
+    assert bool(torch.isfinite(torch.view_as_real(base)).all())
+    assert dev_rel(base.T, base) <= 1e-12 and dev_rel(base.flip(0), base) <= 1e-12 and dev_rel(base.flip(1), base) <= 1e-12
+    phase = complex(np.exp(0.7j))
+    rot = Grid2D(n, 0.1, 1e-3, pumping=P, coeffs=c, u0=0.1 * phase).advance(3).psi[0]
+    assert dev_rel(rot, base * phase) <= 1e-12
+    del rot
+    split = Grid2D(n, 0.1, 1e-3, pumping=P, coeffs=c, u0=0.1).advance(2).advance(1).psi[0]
+    assert bool(torch.equal(split, base))
+
+
+def test_c5_and_c3_shapes_members_are_independent_of_the_batch():
+    """Ensemble configs at their member sizes (1024 x 1024 grids; 1000-node radial systems): a member's result does
+    not depend on which batch it runs in, and matches the oracle on a short horizon."""
+    from nls_b200.engine import Ensemble1D, Grid2D, device_pumping
+    n, iters = 1024, 3
+    radii = np.linspace(2.0, 40.0, 8)
+    m = model_2d(64)
+    c = m.getCoefficients()
+    P = device_pumping(2, "ring", n, 0.1, 20.0, 3.14, radius=radii)
+    many = Grid2D(n, 0.1, 1e-3, batch=8, pumping=P, coeffs=c, u0=0.1).advance(iters).solution()
+    one = Grid2D(n, 0.1, 1e-3, batch=1, pumping=P[5:6], coeffs=c, u0=0.1).advance(iters).solution()[0]
+    assert np.array_equal(many[5], one)
+    want = O.dp.solve_nls_2d(1e-3, 0.1, 5, iters, P[5].cpu().numpy(), c, 0.1 * np.ones((n, n), dtype=complex))
+    assert rel_l2(one, want) <= 1e-10
+    n1 = 1000
+    m1 = model_1d(n1, power=1.0)
+    powers = np.linspace(1.0, 40.0, 64)
+    P1 = device_pumping(1, "ring", n1, 0.1, powers, 3.14, radius=10.0)
+    ens = Ensemble1D(n1, 0.1, 1e-3, batch=64, pumping=P1, coeffs=m1.getCoefficients(), u0=0.1).advance(500).solution()
+    solo = Ensemble1D(n1, 0.1, 1e-3, batch=1, pumping=P1[17:18], coeffs=m1.getCoefficients(), u0=0.1).advance(500).solution()[0]
+    assert np.array_equal(ens[17], solo)
+    want = O.dp.solve_nls(1e-3, 0.1, 5, 500, P1[17].cpu().numpy(), m1.getCoefficients(), 0.1 * np.ones(n1, dtype=complex))
+    assert rel_l2(solo, want) <= 1e-10

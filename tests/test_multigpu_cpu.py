@@ -121,3 +121,39 @@ def test_gloo_slab_run_matches_single_domain_bitwise(tmp_path, world):
     assert np.array_equal(full, single)
     want = O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), m.getCoefficients(), u0)
     assert np.linalg.norm(full - want) / np.linalg.norm(want) <= 1e-12
+
+
+# ---- sweep front-end (nls_b200/sweep.py): sharding and gathering over gloo, the engine replaced by a stub --------
+def _stub_runner(model, kind, n, dx, dt, order, iters, u0, points, keep_fields):
+    return {"tag": np.array([p.pump("power") * 2 + p.pump("radius") for p in points]),
+            "c12": np.array([p.coefficients()[11] for p in points])}
+
+
+def _sweep_points(count):
+    return [dict(power=1.0 + i, radius=0.5 * i, gamma_R=0.1 + 0.01 * i) for i in range(count)]
+
+
+def _sweep_worker(rank, world, port, count, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nls_b200.sweep import run_sweep
+        table = run_sweep(_sweep_points(count), num_nodes=32, num_iters=5, runner=_stub_runner)
+        assert (table is None) == (rank != 0)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "table.npz"), **table)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,count", [(2, 7), (3, 10), (3, 2)])
+def test_sweep_shards_points_and_gathers_in_order(tmp_path, world, count):
+    from nls_b200.sweep import SweepPoint, run_sweep
+    mp.spawn(_sweep_worker, args=(world, _free_port(), count, str(tmp_path)), nprocs=world, join=True)
+    table = np.load(tmp_path / "table.npz")
+    single = run_sweep(_sweep_points(count), num_nodes=32, num_iters=5, runner=_stub_runner)     # no process group
+    assert np.array_equal(table["tag"], single["tag"]) and np.array_equal(table["c12"], single["c12"])
+    want = [SweepPoint(p).pump("power") * 2 + SweepPoint(p).pump("radius") for p in _sweep_points(count)]
+    assert np.array_equal(table["tag"], np.array(want))
+    # per-point coefficients follow nls/model.py:157 (c12 = 1 / (n0 gamma_R)) for the swept gamma_R
+    assert len(set(table["c12"])) == count
