@@ -59,8 +59,9 @@ WORKLOADS = {
 }
 
 
-def build_inputs(name, iters=None, batch=None, n=None):
-    """Synthetic inputs of the named shape (deterministic)."""
+def build_inputs(name, iters=None, batch=None, n=None, members=None):
+    """Synthetic inputs of the named shape (deterministic).  members = (lo, hi): build only that
+    range of an ensemble's members (what one rank owns); w["batch"] stays the size of the whole ensemble."""
     from nls_b200.model import Problem, dimensionless_coefficients
     from nls_b200.pumping import GaussianRingPumping1D, GaussianRingPumping2D
     w = dict(WORKLOADS[name])
@@ -88,22 +89,24 @@ def build_inputs(name, iters=None, batch=None, n=None):
         side = int(round(np.sqrt(B)))
         powers = np.linspace(1.0, 40.0, side)
         gammas = np.geomspace(0.05, 1.0, max(-(-B // side), 1))
-        P = (powers[:, None, None] * unit[None, None, :]) * np.ones((1, len(gammas), 1))
+        lo, hi = members if members else (0, B)
+        idx = np.arange(lo, hi)                       # member i = (power index i // len(gammas), gamma index i % ...)
         C = np.array([dimensionless_coefficients(dict(ORIG, gamma_R=g)) for g in gammas])
-        C = np.broadcast_to(C[None], (side, len(gammas), 23))
-        w.update(pumping=P.reshape(-1, n)[:B], coeffs=C.reshape(-1, 23)[:B].copy(), u0=np.full((B, n), 0.1 + 0j))
+        w.update(pumping=powers[idx // len(gammas), None] * unit[None, :], coeffs=C[idx % len(gammas)].copy(),
+                 u0=np.full((hi - lo, n), 0.1 + 0j))
     elif name == "c4":
         m = Problem().model(model="2d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
                             pumping=GaussianRingPumping2D(power=20.0, radius=200.0, variation=50.0))
         w.update(pumping=m.getPumping()[None], coeffs=coeffs[None], u0=np.full((1, n, n), 0.1 + 0j))
     elif name == "c5":
-        radii = np.linspace(2.0, 40.0, B)
-        P = np.empty((B, n, n))
+        lo, hi = members if members else (0, B)
+        radii = np.linspace(2.0, 40.0, B)[lo:hi]
+        P = np.empty((hi - lo, n, n))
         for b, r in enumerate(radii):
             m = Problem().model(model="2d", dx=0.1, dt=1e-3, u0=0.1, order=5, num_nodes=n, num_iters=w["iters"],
                                 pumping=GaussianRingPumping2D(power=20.0, radius=float(r), variation=3.14))
             P[b] = m.getPumping()
-        w.update(pumping=P, coeffs=np.broadcast_to(coeffs, (B, 23)).copy(), u0=np.full((B, n, n), 0.1 + 0j))
+        w.update(pumping=P, coeffs=np.broadcast_to(coeffs, (hi - lo, 23)).copy(), u0=np.full((hi - lo, n, n), 0.1 + 0j))
     w.update(dx=0.1, dt=1e-3, order=5, name=name)
     return w
 
@@ -241,15 +244,14 @@ def run_engine(args):
     batch = None
     if args.batch:
         batch = args.batch
-    w = build_inputs(name, args.iters, batch, args.n)
+    total_batch = batch if batch else spec["batch"]
+    members = (rank * total_batch // world, (rank + 1) * total_batch // world) if shard else None
+    w = build_inputs(name, args.iters, batch, args.n, members)      # a rank builds only the members it owns
     if args.order:
         w["order"] = args.order
         w["desc"] += " [order overridden: %d]" % args.order
     if shard:
-        lo, hi = rank * w["batch"] // world, (rank + 1) * w["batch"] // world
-        for key in ("pumping", "coeffs", "u0"):
-            w[key] = w[key][lo:hi]
-        w["batch"] = hi - lo
+        w["batch"] = members[1] - members[0]
     iters = w["iters"]
     dev = torch.device("cuda", local)
 
@@ -327,7 +329,8 @@ def run_engine(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
 
-    total_points = points(build_inputs(name, args.iters, batch, args.n)) if shard else points(w) * (1 if slabs else world)
+    n_side = args.n if args.n else spec["n"]
+    total_points = (total_batch * (n_side if spec["dim"] == 1 else n_side * n_side)) if shard else points(w) * (1 if slabs else world)
     work = float(total_points) * iters * args.steps
     value = work / (dev_ms_max * 1e-3)
     peak, peak_src = measured_hbm_peak()
@@ -390,7 +393,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
-    ap.add_argument("--n", type=int, default=None, help="override the grid size (profiling only)")
+    ap.add_argument("--grid-n", dest="n", type=int, default=None, help="override the grid size (profiling only)")
     ap.add_argument("--order", type=int, default=None, help="override the stencil order (profiling only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "resident", "staged"], default="auto", help="2D kernel family")

@@ -48,9 +48,13 @@ def halo_rows(order):
 class SlabPlan(object):
     """Row partition of an n-row grid over `world` ranks and the local buffer geometry of one rank."""
 
-    def __init__(self, n, order, rank, world):
+    def __init__(self, n, order, rank, world, halo_steps=1):
         self.n, self.order, self.rank, self.world = int(n), int(order), int(rank), int(world)
-        self.halo = halo_rows(order)
+        # halo_steps = m: the halo is deep enough for m RK4 steps between two exchanges (the rows a neighbour
+        # owns are recomputed redundantly on a shrinking region: step s of m trusts (m - s) * 4k halo rows)
+        self.halo_steps = max(1, int(halo_steps)) if world > 1 else 1
+        self.step_halo = halo_rows(order)
+        self.halo = self.step_halo * self.halo_steps
         self.row_lo, self.row_hi = shard_range(self.n, rank, world)
         self.rows_local = self.row_hi - self.row_lo
         smallest = min(shard_range(self.n, r, world)[1] - shard_range(self.n, r, world)[0] for r in range(world))
@@ -65,6 +69,13 @@ class SlabPlan(object):
     @property
     def owned(self):
         return self.halo, self.halo + self.rows_local
+
+    def step_rows(self, s):
+        """Local rows to produce in the s-th step (0-based) after an exchange: the rows whose 4k-row neighbourhood
+        is still valid, clipped to the rows inside the global square."""
+        dom_lo, dom_hi = max(0, -self.global_row0), min(self.rows_alloc, self.n - self.global_row0)
+        margin = (s + 1) * self.step_halo
+        return max(margin, dom_lo), min(self.rows_alloc - margin, dom_hi)
 
     def strips(self):
         """(top strip, bottom strip, interior) as local row ranges; strips hold the rows neighbours need."""
@@ -133,6 +144,20 @@ def _cuda_stepper_interleaved(plan, cols, dx, dt, order, coeffs):
     return step
 
 
+def default_halo_steps(n, order, world):
+    """Steps between two halo exchanges for the CUDA steppers.  One exchange per step costs ~150 us of host time
+    (NCCL group + three launches): measured on 8 B200s it bounds the 8192^2 grid at 250 us per step where the
+    kernels need 120.  With a 4x deeper halo one launch per step and one exchange per 4 steps remain; the price
+    is 4k m (m - 1) redundantly computed rows per m steps (2 % of a 1024-row slab)."""
+    if world <= 1:
+        return 1
+    rows = n // world
+    for m in (4, 2):
+        if halo_rows(order) * m * 8 <= rows:
+            return m
+    return 1
+
+
 def _default_cuda_stepper(plan, cols, dx, dt, order, coeffs):
     # slabs large enough for the strip-marching kernel (api.cu: stream_preferred) use the interleaved layout
     lo, hi = plan.owned
@@ -149,7 +174,7 @@ class SlabGrid2D(object):
     """
 
     def __init__(self, n, dx, dt, order=5, pumping=None, coeffs=None, u0=0.1, group=None, device=None, stepper=None,
-                 rank=None, world=None):
+                 rank=None, world=None, halo_steps=None):
         self.group = group
         if rank is not None or world is not None:
             # explicit placement: several slabs emulated inside one process (see advance_emulated)
@@ -157,7 +182,10 @@ class SlabGrid2D(object):
         else:
             self.world = dist.get_world_size(group) if dist.is_initialized() else 1
             self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.plan = SlabPlan(n, order, self.rank, self.world)
+        if halo_steps is None:
+            halo_steps = default_halo_steps(int(n), int(order), self.world) if stepper is None else 1
+        self.plan = SlabPlan(n, order, self.rank, self.world, halo_steps)
+        self.since_exchange = 0          # steps taken since the halos were last refreshed (deep-halo mode)
         self.n, self.dx, self.dt, self.order = int(n), float(dx), float(dt), int(order)
         self.coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
         if self.coeffs.shape != (23,):
@@ -233,7 +261,27 @@ class SlabGrid2D(object):
         top, bottom, interior = p.strips()
         for _ in range(int(iters)):
             src, dst = self.psi[self.cur], self.psi[1 - self.cur]
-            if self.world == 1:
+            if p.halo_steps > 1:
+                # deep halo: one launch per step on the rows that are still valid, one exchange per halo_steps
+                last = self.since_exchange + 1 == p.halo_steps
+                lo, hi = p.step_rows(self.since_exchange)
+                if last and self.on_gpu and hi - lo > 4 * p.halo:
+                    # the step before an exchange: the rows the neighbours need first (side stream), their
+                    # transfer over NVLink overlaps the interior rows (main stream)
+                    main = torch.cuda.current_stream(self.device)
+                    self.side.wait_stream(main)
+                    with torch.cuda.stream(self.side):
+                        self.stepper(src, dst, self.pumping, lo, lo + p.halo)
+                        self.stepper(src, dst, self.pumping, hi - p.halo, hi)
+                        self._exchange(dst)
+                    self.stepper(src, dst, self.pumping, lo + p.halo, hi - p.halo)
+                    main.wait_stream(self.side)
+                else:
+                    self.stepper(src, dst, self.pumping, lo, hi)
+                    if last:
+                        self._exchange(dst)
+                self.since_exchange = 0 if last else self.since_exchange + 1
+            elif self.world == 1:
                 self.stepper(src, dst, self.pumping, *interior)
             elif self.on_gpu:
                 main = torch.cuda.current_stream(self.device)
@@ -260,6 +308,9 @@ class SlabGrid2D(object):
     def compute_step(self):
         """One step of this slab WITHOUT the halo exchange (for in-process emulation of several ranks)."""
         src, dst = self.psi[self.cur], self.psi[1 - self.cur]
+        if self.plan.halo_steps > 1:
+            self.stepper(src, dst, self.pumping, *self.plan.step_rows(self.since_exchange))
+            return dst
         for rows in self.plan.strips():
             if rows:
                 self.stepper(src, dst, self.pumping, *rows)
@@ -276,6 +327,7 @@ class SlabGrid2D(object):
     def set_local_state(self, other_buffer):
         """Overwrite the current state buffer (same layout) -- used by bench.py to reset between runs."""
         self.psi[self.cur].copy_(other_buffer)
+        self.since_exchange = 0
 
     def state_buffer(self):
         return self.psi[self.cur]
@@ -307,6 +359,10 @@ def advance_emulated(slabs, iters):
         new = [g.compute_step() for g in slabs]
         for g, buf in zip(slabs, new):
             p = g.plan
+            g.since_exchange += 1
+            if g.since_exchange < p.halo_steps:
+                continue                      # deep halo: the rows still trusted shrink, no exchange yet
+            g.since_exchange = 0
             if p.up is not None:
                 a, b = p.recv_from_up()
                 c, d = slabs[p.up].plan.send_down()

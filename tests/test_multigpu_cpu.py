@@ -87,18 +87,42 @@ def test_emulated_slabs_are_bitwise_partition_invariant(world):
     assert np.array_equal(full, single)
 
 
+@pytest.mark.parametrize("world,halo_steps,iters", [(2, 2, 9), (3, 2, 8), (2, 3, 7)])
+def test_deep_halo_slabs_are_bitwise_partition_invariant(world, halo_steps, iters):
+    """halo_steps = m: one exchange per m steps, the neighbours' rows recomputed on a shrinking region."""
+    n = 96
+    single, m, u0 = _single_domain(n, iters)
+    slabs = [SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0, stepper=numpy_stepper,
+                        rank=r, world=world, halo_steps=halo_steps) for r in range(world)]
+    assert slabs[0].plan.halo == 8 * halo_steps and slabs[0].plan.step_rows(0)[0] == 8 * halo_steps
+    advance_emulated(slabs, iters)
+    full = np.concatenate([g.local_solution().numpy() for g in slabs], axis=0)
+    assert np.array_equal(full, single)
+    # continuing after a partial macro step keeps working
+    advance_emulated(slabs, 3)
+    again, _, _ = _single_domain(n, iters + 3)
+    assert np.array_equal(np.concatenate([g.local_solution().numpy() for g in slabs], axis=0), again)
+
+
+def test_default_halo_steps():
+    from nls_b200.multigpu import default_halo_steps
+    assert default_halo_steps(8192, 5, 8) == 4 and default_halo_steps(8192, 5, 1) == 1
+    assert default_halo_steps(512, 5, 2) == 4 and default_halo_steps(256, 5, 2) == 2 and default_halo_steps(96, 5, 4) == 1
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, iters, out_dir):
+def _worker(rank, world, port, n, iters, out_dir, halo_steps=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         m, u0 = _problem(n)
-        g = SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0, stepper=numpy_stepper)
+        g = SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0, stepper=numpy_stepper,
+                       halo_steps=halo_steps)
         assert (g.rank, g.world) == (rank, world)
         full = g.advance(iters).gather()
         if rank == 0:
@@ -112,10 +136,10 @@ def _worker(rank, world, port, n, iters, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_gloo_slab_run_matches_single_domain_bitwise(tmp_path, world):
+@pytest.mark.parametrize("world,halo_steps", [(2, 1), (3, 1), (2, 2)])
+def test_gloo_slab_run_matches_single_domain_bitwise(tmp_path, world, halo_steps):
     n, iters = 48, 9
-    mp.spawn(_worker, args=(world, _free_port(), n, iters, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, iters, str(tmp_path), halo_steps), nprocs=world, join=True)
     full = np.load(tmp_path / "full.npy")
     single, m, u0 = _single_domain(n, iters)
     assert np.array_equal(full, single)

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_slabs.py -x -q -m gpu -k "stream or slab" 2>&1 | tail -5 | tee gpurun_out/stream_tests.log
 for n in 8192 4096 2048 1024; do
   for path in stream auto; do
-    timeout 600 python bench.py --workload c4 --n $n --path $path --steps 3 --warmup 3 --no-cpu --iters 40 2>&1 | tail -1 > gpurun_out/bench_n${n}_$path.json
+    timeout 600 python bench.py --workload c4 --grid-n $n --path $path --steps 3 --warmup 3 --no-cpu --iters 40 2>&1 | tail -1 > gpurun_out/bench_n${n}_$path.json
   done
 done
 timeout 600 python bench.py --workload c5 --batch 32 --path stream --steps 3 --warmup 3 --no-cpu 2>&1 | tail -1 > gpurun_out/bench_c5_stream.json
