@@ -38,11 +38,11 @@ BYTES_PER_POINT_STEP = 40.0      # read psi 16 + read P 8 + write 
 # `ncu --set full` captures summarised under profiles/ (round 1, default kernels).  C2's working set is
 # L2-resident: the figure is the cold-cache replay ncu measures, in steady state it is ~0.
 NCU_TRAFFIC = {
-    "c2": (6.34e6, "profiles/r1_ncu_tma32_c2_512.txt (cold L2 under ncu; L2-resident in steady state)"),
+    "c2": (6.32e6, "profiles/r1_ncu_tma64_pdl_c2_512_default.txt (cold L2 under ncu; L2-resident in steady state)"),
     "c4": (2.714e9, "profiles/r1_ncu_stream_c4_8192.txt"),
 }
 DOMINANT_KERNEL = {"c1": "rk4_1d_resident (whole time loop, one launch)", "c3": "rk4_1d_resident (whole time loop, one launch)",
-                   "c2": "rk4_step_fused_kernel (TMA tile kernel, one RK4 step per launch)",
+                   "c2": "rk4_step_fused_kernel (TMA tile kernel, 32x64 tiles, one RK4 step per launch)",
                    "c4": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)",
                    "c5": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)"}
 

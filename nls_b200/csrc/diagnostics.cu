@@ -87,50 +87,59 @@ struct WeightsK {
     double wy[2 * K + 1];
 };
 
+// A CTA walks over 64 x 16-node tiles (thread = one column, four rows of the tile): the y neighbours of a tile
+// stay in L1 instead of being fetched from L2 once per row.
+constexpr int kTileW = 64, kTileH = 16;
+
 template <int K>
 __global__ void __launch_bounds__(kThreads)
 diagnostics_2d_kernel(int rows, int cols, double area, WeightsK<K> w, const double *__restrict__ pumping,
                       const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial)
 {
-    const size_t member = blockIdx.y;
+    const size_t member = blockIdx.x;
     const size_t plane = (size_t)rows * cols;
     const double2 *src = u + member * plane;
     const double *P = pumping + member * plane;
     const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
     Acc a = acc_zero();
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < plane; t += stride) {
-        const int y = (int)(t / cols), x = (int)(t % cols);
-        const double2 centre = src[t];
-        double lr = w.wx[K] * centre.x, li = w.wx[K] * centre.y;       // same tap order as stage_2d_kernel
+    const int tiles_x = (cols + kTileW - 1) / kTileW, tiles_y = (rows + kTileH - 1) / kTileH;
+    const int tx = threadIdx.x % kTileW, ty = threadIdx.x / kTileW;
+    for (int tile = blockIdx.y; tile < tiles_x * tiles_y; tile += gridDim.y) {
+        const int x = (tile % tiles_x) * kTileW + tx;
+        if (x >= cols) continue;
+        for (int y = (tile / tiles_x) * kTileH + ty; y < rows && y < (tile / tiles_x + 1) * kTileH; y += kThreads / kTileW) {
+            const size_t t = (size_t)y * cols + x;
+            const double2 centre = src[t];
+            double lr = w.wx[K] * centre.x, li = w.wx[K] * centre.y;       // same tap order as stage_2d_kernel
 #pragma unroll
-        for (int s = 1; s <= K; ++s) {
-            if (x - s >= 0) {
-                const double2 v = src[t - s];
-                lr = fma(w.wx[K - s], v.x, lr);
-                li = fma(w.wx[K - s], v.y, li);
+            for (int s = 1; s <= K; ++s) {
+                if (x - s >= 0) {
+                    const double2 v = src[t - s];
+                    lr = fma(w.wx[K - s], v.x, lr);
+                    li = fma(w.wx[K - s], v.y, li);
+                }
+                if (x + s < cols) {
+                    const double2 v = src[t + s];
+                    lr = fma(w.wx[K + s], v.x, lr);
+                    li = fma(w.wx[K + s], v.y, li);
+                }
+                if (y - s >= 0) {
+                    const double2 v = src[t - (size_t)s * cols];
+                    lr = fma(w.wy[K - s], v.x, lr);
+                    li = fma(w.wy[K - s], v.y, li);
+                }
+                if (y + s < rows) {
+                    const double2 v = src[t + (size_t)s * cols];
+                    lr = fma(w.wy[K + s], v.x, lr);
+                    li = fma(w.wy[K + s], v.y, li);
+                }
             }
-            if (x + s < cols) {
-                const double2 v = src[t + s];
-                lr = fma(w.wx[K + s], v.x, lr);
-                li = fma(w.wx[K + s], v.y, li);
-            }
-            if (y - s >= 0) {
-                const double2 v = src[t - (size_t)s * cols];
-                lr = fma(w.wy[K - s], v.x, lr);
-                li = fma(w.wy[K - s], v.y, li);
-            }
-            if (y + s < rows) {
-                const double2 v = src[t + (size_t)s * cols];
-                lr = fma(w.wy[K + s], v.x, lr);
-                li = fma(w.wy[K + s], v.y, li);
-            }
+            const double cp = c.c12 * P[t];
+            accumulate(a, c, cp, centre, rhs_point(c, cp, centre, lr, li), 1.0, area);
         }
-        const double cp = c.c12 * P[t];
-        accumulate(a, c, cp, centre, rhs_point(c, cp, centre, lr, li), 1.0, area);
     }
     a = block_reduce(a);
-    if (threadIdx.x == 0) partial[member * gridDim.x + blockIdx.x] = a;
+    if (threadIdx.x == 0) partial[member * gridDim.y + blockIdx.y] = a;
 }
 
 template <int M>
@@ -139,13 +148,13 @@ diagnostics_1d_kernel(int n, double dx, const double *__restrict__ taps, const d
                       const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial)
 {
     constexpr int K = (M - 1) / 2;
-    const size_t member = blockIdx.y;
+    const size_t member = blockIdx.x;          // members on the x axis of the grid: ensembles exceed 65535
     const double2 *um = u + member * n;
     const double *P = pumping + member * n;
     const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
     const double ring = n > 1 ? (n * dx) / (n - 1) : 0.0;              // spacing of linspace(0, n dx, n)
     Acc a = acc_zero();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         double lr = 0.0, li = 0.0;
 #pragma unroll
         for (int t = 0; t < M; ++t) {
@@ -162,7 +171,7 @@ diagnostics_1d_kernel(int n, double dx, const double *__restrict__ taps, const d
         accumulate(a, c, cp, um[i], rhs_point(c, cp, um[i], lr, li), w, wd);
     }
     a = block_reduce(a);
-    if (threadIdx.x == 0) partial[member * gridDim.x + blockIdx.x] = a;
+    if (threadIdx.x == 0) partial[member * gridDim.y + blockIdx.y] = a;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -187,11 +196,12 @@ finish_diagnostics_kernel(int nparts, const Acc *__restrict__ partial, double *_
     }
 }
 
-int parts_for(size_t npts, int batch)
+int parts_for(size_t units, int batch)      // units: CTA-sized pieces of work of one member
 {
-    size_t blocks = (npts + kThreads - 1) / kThreads;
-    // enough CTAs to fill the GPU across the batch, at most 592 partials per member
-    size_t cap = batch >= 148 ? 8 : 592 / (size_t)batch + 1;
+    size_t blocks = units;
+    // enough CTAs to fill the GPU across the batch (592 = 4 per SM), at most 592 partials per member; a large
+    // ensemble gets one CTA per member (one block reduction per member instead of one per 256 nodes)
+    size_t cap = batch >= 592 ? 1 : 592 / (size_t)batch + 1;
     if (cap > 592) cap = 592;
     if (blocks > cap) blocks = cap;
     return blocks ? (int)blocks : 1;
@@ -216,9 +226,8 @@ int launch_diagnostics_2d(int batch, int rows, int cols, int order, double dx, c
                           const double *pumping, const double *coeffs, const double2 *u, void *scratch, double *out8,
                           cudaStream_t stream)
 {
-    if (batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", batch);
-    const int parts = parts_for((size_t)rows * cols, batch);
-    const dim3 grid((unsigned)parts, (unsigned)batch);
+    const int parts = parts_for((size_t)((cols + kTileW - 1) / kTileW) * ((rows + kTileH - 1) / kTileH), batch);
+    const dim3 grid((unsigned)batch, (unsigned)parts);
     Acc *partial = static_cast<Acc *>(scratch);
     switch (order) {
     case 3: diagnostics_2d_kernel<1><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<1>(w), pumping, coeffs, u, partial); break;
@@ -234,9 +243,8 @@ int launch_diagnostics_2d(int batch, int rows, int cols, int order, double dx, c
 int launch_diagnostics_1d(int batch, int n, int order, double dx, const double *taps, const double *pumping,
                           const double *coeffs, const double2 *u, void *scratch, double *out8, cudaStream_t stream)
 {
-    if (batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", batch);
-    const int parts = parts_for((size_t)n, batch);
-    const dim3 grid((unsigned)parts, (unsigned)batch);
+    const int parts = parts_for(((size_t)n + kThreads - 1) / kThreads, batch);
+    const dim3 grid((unsigned)batch, (unsigned)parts);
     Acc *partial = static_cast<Acc *>(scratch);
     switch (order) {
     case 3: diagnostics_1d_kernel<3><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;

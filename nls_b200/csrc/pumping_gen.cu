@@ -61,11 +61,11 @@ __global__ void pumping_2d_kernel(int kind, int n, double start, double stop, do
 __global__ void pumping_1d_kernel(int kind, int n, double start, double stop, double step,
                                   const double *__restrict__ params, double *__restrict__ out)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;      // members on the x axis: ensembles exceed 65535
     if (j >= n) return;
-    const double *p = params + 5 * (size_t)blockIdx.y;
+    const double *p = params + 5 * (size_t)blockIdx.x;
     const double x = linspace_at(j, n, start, stop, step);
-    out[(size_t)blockIdx.y * n + j] = kind == 0 ? gauss(p[0], __dsub_rn(x, p[1]), __dsub_rn(0.0, p[2]), p[3])
+    out[(size_t)blockIdx.x * n + j] = kind == 0 ? gauss(p[0], __dsub_rn(x, p[1]), __dsub_rn(0.0, p[2]), p[3])
                                                 : ring(p[0], p[4], p[3], x);
 }
 
@@ -75,12 +75,13 @@ __global__ void pumping_1d_kernel(int kind, int n, double start, double stop, do
 int launch_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_dev, double *out,
                             cudaStream_t stream)
 {
-    if (batch > 65535 || n > 65535) return fail(NLSB_ESIZE, "pumping profiles: batch and n must not exceed 65535");
+    if (n > 65535 || (dim == 2 && batch > 65535))
+        return fail(NLSB_ESIZE, "pumping profiles: n (and the batch of 2D profiles) must not exceed 65535");
     const double right = dim == 1 ? n * dx : n * dx / 2;
     const double start = dim == 1 ? 0.0 : -right, stop = right;
     const double step = n > 1 ? (stop - start) / (n - 1) : 0.0;
     if (dim == 1) {
-        const dim3 grid((n + 127) / 128, batch);
+        const dim3 grid(batch, (n + 127) / 128);
         pumping_1d_kernel<<<grid, 128, 0, stream>>>(kind, n, start, stop, step, params_dev, out);
     } else {
         const dim3 grid((n + 127) / 128, n, batch);
