@@ -108,6 +108,25 @@ def _diagnostics_dict(out8):
             "max_density": d[:, 6].copy(), "max_reservoir": d[:, 7].copy()}
 
 
+def _advance_until(engine, rel_tol, check_every, max_iters, quantity):
+    """Shared body of ``advance_until``: chunks of ``check_every`` steps, one device-side reduction per chunk."""
+    if check_every < 1 or max_iters < 0:
+        raise ValueError("check_every must be positive and max_iters non-negative")
+    previous = engine.diagnostics()[quantity]
+    done, history = 0, [previous]
+    while done < max_iters:
+        chunk = min(int(check_every), int(max_iters) - done)
+        engine.advance(chunk)
+        done += chunk
+        current = engine.diagnostics()[quantity]
+        history.append(current)
+        change = np.max(np.abs(current - previous) / np.maximum(np.abs(current), np.finfo(float).tiny))
+        if change <= rel_tol:
+            return done, True, history
+        previous = current
+    return done, False, history
+
+
 class Ensemble1D(object):
     """``batch`` independent radial systems of ``n`` nodes sharing dx, dt and the stencil order.
 
@@ -150,6 +169,14 @@ class Ensemble1D(object):
             _lib.call("nlsb_dev_hamiltonian_1d", self.batch, self.n, self.order, _dptr(self.taps), _dptr(self.pumping),
                       _dptr(self.coeffs), _dptr(u), _dptr(v), _stream())
         return v
+
+    def advance_until(self, rel_tol=1e-6, check_every=100, max_iters=100000, quantity="particles"):
+        """Advance in chunks of ``check_every`` steps until ``quantity`` (a key of ``diagnostics()``) changes by at
+        most ``rel_tol`` (relative, worst member) over a chunk, or ``max_iters`` steps were taken.  The field never
+        leaves the device: per chunk 8 doubles per member cross the bus.  The reference has no stopping test
+        (fixed ``iters``, nls.f90:705-734); ``tools/check.py:28-63`` does this loop by hand with a full
+        solve -> copy -> chemical potential round trip per chunk.  Returns (steps taken, converged, history)."""
+        return _advance_until(self, rel_tol, check_every, max_iters, quantity)
 
     def diagnostics(self):
         """Chemical potential, damping integral, particle number, peak density and peak reservoir of every member,
@@ -230,6 +257,14 @@ class Grid2D(object):
             _lib.call("nlsb_dev_hamiltonian_2d", self.batch, self.rows, self.cols, self.order, self._w(self.wx),
                       self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), _dptr(u), _dptr(v), _stream())
         return v
+
+    def advance_until(self, rel_tol=1e-6, check_every=100, max_iters=100000, quantity="particles"):
+        """Advance in chunks of ``check_every`` steps until ``quantity`` (a key of ``diagnostics()``) changes by at
+        most ``rel_tol`` (relative, worst member) over a chunk, or ``max_iters`` steps were taken.  The field never
+        leaves the device: per chunk 8 doubles per member cross the bus.  The reference has no stopping test
+        (fixed ``iters``, nls.f90:705-734); ``tools/check.py:28-63`` does this loop by hand with a full
+        solve -> copy -> chemical potential round trip per chunk.  Returns (steps taken, converged, history)."""
+        return _advance_until(self, rel_tol, check_every, max_iters, quantity)
 
     def diagnostics(self):
         """As ``Ensemble1D.diagnostics`` for 2D grids (area element dx^2, chemical potential weight 1)."""

@@ -294,3 +294,20 @@ def test_c5_and_c3_shapes_members_are_independent_of_the_batch():
     assert np.array_equal(ens[17], solo)
     want = O.dp.solve_nls(1e-3, 0.1, 5, 500, P1[17].cpu().numpy(), m1.getCoefficients(), 0.1 * np.ones(n1, dtype=complex))
     assert rel_l2(solo, want) <= 1e-10
+
+
+def test_advance_until_stops_on_a_device_side_criterion():
+    """Steady-state stopping test built on the device diagnostics: same state as plain advance."""
+    from nls_b200.engine import Ensemble1D
+    m = model_1d(200)
+    a = Ensemble1D(200, m.dx, m.dt, batch=2, pumping=np.array([m.getPumping(), 1.5 * m.getPumping()]),
+                   coeffs=m.getCoefficients(), u0=0.1)
+    steps, converged, history = a.advance_until(rel_tol=1e-3, check_every=250, max_iters=20000)
+    assert converged and steps % 250 == 0 and 250 <= steps < 20000 and len(history) == steps // 250 + 1
+    last, prev = history[-1], history[-2]
+    assert np.max(np.abs(last - prev) / np.abs(last)) <= 1e-3
+    b = Ensemble1D(200, m.dx, m.dt, batch=2, pumping=np.array([m.getPumping(), 1.5 * m.getPumping()]),
+                   coeffs=m.getCoefficients(), u0=0.1).advance(steps)
+    assert np.array_equal(a.solution(), b.solution())
+    steps, converged, _ = b.advance_until(rel_tol=0.0, check_every=7, max_iters=20)
+    assert steps == 20 and not converged
