@@ -137,7 +137,7 @@ void enqueue_step_2d(int batch, int rows, int cols, int order, double dt, const 
     stage(kStageLast, ya, psi, 0.0);
 }
 
-// 0 = automatic (= 4), 1 = per-stage kernels, 2 / 3 = fused 32x32 / 32x64 tiles filled with plain loads from
+// 0 = automatic (see below), 1 = per-stage kernels, 2 / 3 = fused 32x32 / 32x64 tiles filled with plain loads from
 // interleaved psi, 4 / 5 = fused 32x32 / 32x64 tiles filled by TMA from the planar working copy, one launch
 // per step, 6 / 7 = as 4 / 5 but the whole time loop in one persistent, neighbour-synchronised launch when
 // every tile is resident at once (experimental: measured slower than per-step launches),

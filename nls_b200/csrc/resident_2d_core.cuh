@@ -5,7 +5,7 @@
 // (:841-870; cross stencil of make_laplacian_2d :297-385; reservoir :829-839) and the RK4 update.
 //
 // Why: a grid like BASELINE config 2 (512 x 512) is 1771 nodes per SM.  One launch per step (fused_2d.cu)
-// spends most of a step on launch latency, tile fill and the redundant halo ring (1.43x) -- 13.6 us per step.
+// spends most of a step on launch latency, tile fill and the redundant halo ring (1.43x) -- about 8 us per step.
 // Here the grid is cut into one PATCH per CTA (<= 128 columns x <= 15 rows; 4 x 37 = 148 patches for 512^2),
 // every thread keeps the RK accumulator and the current stage input of its 5 nodes in registers (psi and c12*P in
 // thread-private shared-memory slots) for all steps, and nothing is recomputed.  Per stage a CTA

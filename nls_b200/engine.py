@@ -42,7 +42,9 @@ def _stream():
 
 
 def set_2d_path(path):
-    """Select the 2D kernels: "auto" / "fused" (one launch per RK step) or "staged" (one per RK stage)."""
+    """Select the 2D kernels (C ABI ``nlsb_set_2d_path``): "auto" (strip-marching kernel from 2^20 nodes, TMA tile
+    kernel below), "stream", "tma32" / "tma64" / "fused32" / "fused64" (tile kernel variants), "staged" (one launch
+    per RK stage), "tma32_persistent" / "tma64_persistent" / "resident" (experimental whole-loop kernels)."""
     code = {"auto": 0, "staged": 1, "fused": 4, "fused32": 2, "fused64": 3, "tma32": 4, "tma64": 5,
             "tma32_persistent": 6, "tma64_persistent": 7, "stream": 8, "resident": 9}[path]
     _lib.call("nlsb_set_2d_path", code)
