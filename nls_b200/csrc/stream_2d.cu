@@ -81,7 +81,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *map, uint3
 }
 
 template <typename C, bool UNIFORM>
-__global__ void __launch_bounds__(C::T, 1)
+__global__ void __launch_bounds__(C::T, C::CTAS_PER_SM)
 rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ StreamWeights<C::K> wa,
                   const __grid_constant__ TensorMap map, const __grid_constant__ TensorMap map_p)
 {
@@ -262,7 +262,7 @@ int chunk_rows_for(int out_rows, int strips, int batch)
         return e ? std::atoi(e) : 0;
     }();
     if (forced >= 6 * C::K + C::U) return C::chunk_rows(forced);
-    const long long sms = sm_count();
+    const long long sms = (long long)sm_count() * C::CTAS_PER_SM;      // CTAs resident at once
     int best_h = C::chunk_rows(140);
     double best_cost = 0.0;
     for (int m = (6 * C::K) / C::U + 2; m <= 96; ++m) {
@@ -313,12 +313,24 @@ int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t 
 template <int K>
 struct StreamShape {
     using Wide = Cfg<K, (K == 3) ? 192 : 256>;      // order 7: the rings of 256 columns do not fit in shared memory
+    using Narrow = Cfg<K, 128>;                     // two CTAs per SM: their barriers and load bursts are independent
 };
 
 template <int K>
 int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
 {
     using C = typename StreamShape<K>::Wide;
+    using N = typename StreamShape<K>::Narrow;
+    static const int force = [] {
+        const char *e = std::getenv("NLSB_STREAM_T");         // tuning knob: 128 or 256
+        return e ? std::atoi(e) : 0;
+    }();
+    // Two 128-thread CTAs per SM overlap each other's load bursts and barriers (+3 % per unit of work, measured) but
+    // sweep T / W = 128 / 112 columns per useful column instead of 256 / 240: taken where that costs nothing
+    // (1024-wide ensemble members: 10 x 128 = 5 x 256 columns).
+    const long long narrow = (long long)((s.cols + N::W - 1) / N::W) * N::T, wide = (long long)((s.cols + C::W - 1) / C::W) * C::T;
+    if (force == 128 || (force == 0 && K != 3 && narrow <= wide))
+        return s.uniform ? launch_stream_cfg<N, true>(s, w, stream) : launch_stream_cfg<N, false>(s, w, stream);
     return s.uniform ? launch_stream_cfg<C, true>(s, w, stream) : launch_stream_cfg<C, false>(s, w, stream);
 }
 

@@ -43,6 +43,7 @@ struct Cfg {
     static constexpr int NW = 2 * K_ + 1;       // taps per axis = period of the y windows and of the stage rings
     static constexpr int U = 2 * NW;            // unroll of the march = period of the psi / acc / cp windows
     static constexpr int RB = NW, NB = 4;       // rows per TMA batch, batches in the psi ring
+    static constexpr int CTAS_PER_SM = T_ <= 128 ? 2 : 1;   // register budget: 65536 / (T * CTAS_PER_SM) >= 255
     static constexpr int HALO = 4 * K_;         // frame columns each side of the strip
     static constexpr int W = T_ - 2 * HALO;     // columns a strip produces
     static constexpr int RING = RB * NB;        // rows of the psi ring (= 2U)

@@ -89,6 +89,7 @@ extern "C" int emu_stream_step(int order, int threads, int rows, int cols, int g
     }
     EMU_CASE(1, 256)
     EMU_CASE(2, 256)
+    EMU_CASE(2, 128)
     EMU_CASE(3, 192)
     EMU_CASE(1, 64)
     EMU_CASE(2, 64)

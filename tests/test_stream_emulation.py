@@ -61,7 +61,7 @@ def _steps(emu, order, threads, u0, P, coeffs, dt, dx, steps, chunk_rows=0, rows
     return a
 
 
-@pytest.mark.parametrize("order,n,threads,chunk_rows", [(5, 40, 64, 0), (5, 131, 64, 0), (5, 300, 256, 0),
+@pytest.mark.parametrize("order,n,threads,chunk_rows", [(5, 40, 64, 0), (5, 131, 64, 0), (5, 300, 256, 0), (5, 300, 128, 0),
                                                         (5, 97, 64, 28), (5, 7, 64, 0), (3, 131, 64, 0),
                                                         (3, 300, 256, 0), (7, 131, 64, 0), (7, 300, 192, 0)])
 def test_emulated_stream_kernel_matches_oracle(emu, order, n, threads, chunk_rows):
