@@ -39,8 +39,11 @@ BYTES_PER_POINT_STEP = 40.0      # read psi 16 + read P 8 + write 
 # L2-resident: the figure is the cold-cache replay ncu measures, in steady state it is ~0.
 NCU_TRAFFIC = {
     "c2": (6.32e6, "profiles/r1_ncu_tma64_pdl_c2_512_default.txt (cold L2 under ncu; L2-resident in steady state)"),
-    "c4": (2.714e9, "profiles/r1_ncu_stream_c4_8192.txt"),
+    "c4": (2.716e9, "profiles/r1_ncu_stream_c4_8192.txt"),
 }
+# FP64-pipe utilisation of the dominant kernel (sm__pipe_fp64_cycles_active, same ncu captures): the path is bound
+# by FP64 issue + shared-memory traffic, not by HBM -- reported beside the HBM roofline fraction.
+NCU_FP64_PIPE_PCT = {"c2": 39.6, "c3": 67.4, "c4": 66.1}
 DOMINANT_KERNEL = {"c1": "rk4_1d_resident (whole time loop, one launch)", "c3": "rk4_1d_resident (whole time loop, one launch)",
                    "c2": "rk4_step_fused_kernel (TMA tile kernel, 32x64 tiles, one RK4 step per launch)",
                    "c4": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)",
@@ -356,6 +359,7 @@ def run_engine(args):
         "gpu_launches": int(t[2]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src,
+                     "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(name) if args.path == "auto" else None,
                      "kernel": DOMINANT_KERNEL[name],
                      "algorithmic_bytes_per_launch": bytes_per_launch,
                      "avg_launch_us": 1e3 * dev_ms_max / dominant_launches,

@@ -81,6 +81,20 @@ __device__ __forceinline__ void accumulate(Acc &a, const RhsCoeffs &c, double cp
     a.m[1] = fmax(a.m[1], res);
 }
 
+// A CTA's reduced sums: a partial for the finishing launch, or -- when the member has a single CTA -- the result.
+__device__ __forceinline__ void emit(const Acc &a, size_t member, Acc *partial, double *out8)
+{
+    if (gridDim.y > 1) {
+        partial[member * gridDim.y + blockIdx.y] = a;
+        return;
+    }
+    double *o = out8 + member * 8;
+#pragma unroll
+    for (int i = 0; i < kSums; ++i) o[i] = a.s[i];
+    o[6] = a.m[0];
+    o[7] = a.m[1];
+}
+
 template <int K>
 struct WeightsK {
     double wx[2 * K + 1];
@@ -94,7 +108,8 @@ constexpr int kTileW = 64, kTileH = 16;
 template <int K>
 __global__ void __launch_bounds__(kThreads)
 diagnostics_2d_kernel(int rows, int cols, double area, WeightsK<K> w, const double *__restrict__ pumping,
-                      const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial)
+                      const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial,
+                      double *__restrict__ out8)
 {
     const size_t member = blockIdx.x;
     const size_t plane = (size_t)rows * cols;
@@ -139,13 +154,14 @@ diagnostics_2d_kernel(int rows, int cols, double area, WeightsK<K> w, const doub
         }
     }
     a = block_reduce(a);
-    if (threadIdx.x == 0) partial[member * gridDim.y + blockIdx.y] = a;
+    if (threadIdx.x == 0) emit(a, member, partial, out8);
 }
 
 template <int M>
 __global__ void __launch_bounds__(kThreads)
 diagnostics_1d_kernel(int n, double dx, const double *__restrict__ taps, const double *__restrict__ pumping,
-                      const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial)
+                      const double *__restrict__ coeffs, const double2 *__restrict__ u, Acc *__restrict__ partial,
+                      double *__restrict__ out8)
 {
     constexpr int K = (M - 1) / 2;
     const size_t member = blockIdx.x;          // members on the x axis of the grid: ensembles exceed 65535
@@ -171,7 +187,7 @@ diagnostics_1d_kernel(int n, double dx, const double *__restrict__ taps, const d
         accumulate(a, c, cp, um[i], rhs_point(c, cp, um[i], lr, li), w, wd);
     }
     a = block_reduce(a);
-    if (threadIdx.x == 0) partial[member * gridDim.y + blockIdx.y] = a;
+    if (threadIdx.x == 0) emit(a, member, partial, out8);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -230,13 +246,13 @@ int launch_diagnostics_2d(int batch, int rows, int cols, int order, double dx, c
     const dim3 grid((unsigned)batch, (unsigned)parts);
     Acc *partial = static_cast<Acc *>(scratch);
     switch (order) {
-    case 3: diagnostics_2d_kernel<1><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<1>(w), pumping, coeffs, u, partial); break;
-    case 5: diagnostics_2d_kernel<2><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<2>(w), pumping, coeffs, u, partial); break;
-    case 7: diagnostics_2d_kernel<3><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<3>(w), pumping, coeffs, u, partial); break;
+    case 3: diagnostics_2d_kernel<1><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<1>(w), pumping, coeffs, u, partial, out8); break;
+    case 5: diagnostics_2d_kernel<2><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<2>(w), pumping, coeffs, u, partial, out8); break;
+    case 7: diagnostics_2d_kernel<3><<<grid, kThreads, 0, stream>>>(rows, cols, dx * dx, pack<3>(w), pumping, coeffs, u, partial, out8); break;
     default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
     }
-    finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, partial, out8);
-    count_launches(2);
+    if (parts > 1) finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, partial, out8);
+    count_launches(parts > 1 ? 2 : 1);
     return (int)cudaGetLastError();
 }
 
@@ -247,13 +263,13 @@ int launch_diagnostics_1d(int batch, int n, int order, double dx, const double *
     const dim3 grid((unsigned)batch, (unsigned)parts);
     Acc *partial = static_cast<Acc *>(scratch);
     switch (order) {
-    case 3: diagnostics_1d_kernel<3><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;
-    case 5: diagnostics_1d_kernel<5><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;
-    case 7: diagnostics_1d_kernel<7><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial); break;
+    case 3: diagnostics_1d_kernel<3><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial, out8); break;
+    case 5: diagnostics_1d_kernel<5><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial, out8); break;
+    case 7: diagnostics_1d_kernel<7><<<grid, kThreads, 0, stream>>>(n, dx, taps, pumping, coeffs, u, partial, out8); break;
     default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
     }
-    finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, partial, out8);
-    count_launches(2);
+    if (parts > 1) finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, partial, out8);
+    count_launches(parts > 1 ? 2 : 1);
     return (int)cudaGetLastError();
 }
 
