@@ -170,6 +170,12 @@ int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double 
                     const double *wy, const double *pumping, const double *coeffs,
                     const double *shared_coeffs_host, double *psi,
                     void *workspace, size_t workspace_bytes, nlsb_stream_t stream);
+/* Which kernel nlsb_dev_rk4_2d would use for this problem under the current nlsb_set_2d_path, and its launch
+ * geometry (host arithmetic only, needs no device): *kernel = 0 tile kernel 32x32, 1 tile kernel 32x64,
+ * 2 strip-marching kernel (then *threads per CTA, *strips of columns, *chunk_rows per CTA), 3 per-stage kernels,
+ * 4 register-resident kernel (if the grid fits, else 0). */
+int nlsb_dev_rk4_2d_plan(int batch, int rows, int cols, int order, int *kernel, int *threads, int *strips,
+                         int *chunk_rows);
 /* One whole RK4 step of ONE slab of a 2D grid that is decomposed along its slow (row) axis.
  * psi_in / psi_out / pumping are local arrays of rows_alloc x cols nodes (distinct in/out buffers)
  * whose row 0 is global row `global_row0` (negative when the slab starts with halo rows above the

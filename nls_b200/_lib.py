@@ -66,6 +66,7 @@ PROTOTYPES = {
     "nlsb_dev_hamiltonian_2d": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "nlsb_dev_cross_matvec_2d": (_I, [_I, _I, _I, _P, _P, _P, _P, _F, _P]),
     "nlsb_dev_reservoir": (_I, [_Z, _P, _P, _P, _P, _P]),
+    "nlsb_dev_rk4_2d_plan": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "nlsb_dev_pumping_profiles": (_I, [_I, _I, _I, _I, _F, _P, _P, _P]),
     "nlsb_dev_diagnostics_scratch": (_Z, [_I]),
     "nlsb_dev_diagnostics_1d": (_I, [_I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),

@@ -932,6 +932,32 @@ int nlsb_dev_cross_matvec_2d(int rows, int cols, int order, const double *wx, co
     return 0;
 }
 
+int nlsb_dev_rk4_2d_plan(int batch, int rows, int cols, int order, int *kernel, int *threads, int *strips,
+                         int *chunk_rows)
+{
+    if (!kernel || !threads || !strips || !chunk_rows || batch < 1) return fail(NLSB_EINVAL, "dev_rk4_2d_plan: bad arguments");
+    NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
+    const int path = g_path_2d.load();
+    *strips = *chunk_rows = 0;
+    if (path == 8 || (path == 0 && stream_preferred(order, batch, rows, cols))) {
+        if (cols & 1) {                       // the streaming launcher hands odd widths to the 32x32 tile kernel
+            *kernel = 0; *threads = 256;
+            return 0;
+        }
+        *kernel = 2;
+        return stream_2d_plan(order, batch, rows, cols, threads, strips, chunk_rows);
+    }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaGetLastError();
+    const long long small = (long long)((cols + 31) / 32) * ((rows + 31) / 32) * batch;
+    const long long tall = (long long)((cols + 31) / 32) * ((rows + 63) / 64) * batch;
+    const bool tall_tiles = path == 3 || path == 5 || path == 7 || (path == 0 && order != 7 && small > sms && tall <= sms);
+    *kernel = path == 1 ? 3 : path == 9 ? 4 : tall_tiles ? 1 : 0;
+    *threads = tall_tiles ? 512 : 256;
+    return 0;
+}
+
 int nlsb_dev_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_host, double *out,
                               nlsb_stream_t stream)
 {

@@ -316,8 +316,11 @@ struct StreamShape {
     using Narrow = Cfg<K, 128>;                     // two CTAs per SM: their barriers and load bursts are independent
 };
 
+// Two 128-thread CTAs per SM overlap each other's load bursts and barriers (+3 % per unit of work, measured) but
+// sweep T / W = 128 / 112 columns per useful column instead of 256 / 240: taken where that costs nothing
+// (1024-wide ensemble members: 10 x 128 = 5 x 256 columns).
 template <int K>
-int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+bool narrow_shape(int cols)
 {
     using C = typename StreamShape<K>::Wide;
     using N = typename StreamShape<K>::Narrow;
@@ -325,16 +328,44 @@ int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t st
         const char *e = std::getenv("NLSB_STREAM_T");         // tuning knob: 128 or 256
         return e ? std::atoi(e) : 0;
     }();
-    // Two 128-thread CTAs per SM overlap each other's load bursts and barriers (+3 % per unit of work, measured) but
-    // sweep T / W = 128 / 112 columns per useful column instead of 256 / 240: taken where that costs nothing
-    // (1024-wide ensemble members: 10 x 128 = 5 x 256 columns).
-    const long long narrow = (long long)((s.cols + N::W - 1) / N::W) * N::T, wide = (long long)((s.cols + C::W - 1) / C::W) * C::T;
-    if (force == 128 || (force == 0 && K != 3 && narrow <= wide))
+    const long long narrow = (long long)((cols + N::W - 1) / N::W) * N::T, wide = (long long)((cols + C::W - 1) / C::W) * C::T;
+    return force == 128 || (force == 0 && K != 3 && narrow <= wide);
+}
+
+template <int K>
+int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    using C = typename StreamShape<K>::Wide;
+    using N = typename StreamShape<K>::Narrow;
+    if (narrow_shape<K>(s.cols))
         return s.uniform ? launch_stream_cfg<N, true>(s, w, stream) : launch_stream_cfg<N, false>(s, w, stream);
     return s.uniform ? launch_stream_cfg<C, true>(s, w, stream) : launch_stream_cfg<C, false>(s, w, stream);
 }
 
+template <int K>
+void plan_k(int batch, int out_rows, int cols, int *threads, int *strips, int *chunk_rows)
+{
+    using C = typename StreamShape<K>::Wide;
+    using N = typename StreamShape<K>::Narrow;
+    if (narrow_shape<K>(cols)) {
+        *threads = N::T; *strips = (cols + N::W - 1) / N::W; *chunk_rows = chunk_rows_for<N>(out_rows, *strips, batch);
+    } else {
+        *threads = C::T; *strips = (cols + C::W - 1) / C::W; *chunk_rows = chunk_rows_for<C>(out_rows, *strips, batch);
+    }
+}
+
 }  // namespace
+
+// The launch geometry launch_rk4_step_stream_2d would use (host arithmetic only; needs no device).
+int stream_2d_plan(int order, int batch, int out_rows, int cols, int *threads, int *strips, int *chunk_rows)
+{
+    switch (order) {
+    case 3: plan_k<1>(batch, out_rows, cols, threads, strips, chunk_rows); return 0;
+    case 5: plan_k<2>(batch, out_rows, cols, threads, strips, chunk_rows); return 0;
+    case 7: plan_k<3>(batch, out_rows, cols, threads, strips, chunk_rows); return 0;
+    }
+    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
 
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
 {

@@ -105,3 +105,29 @@ def test_compute_fails_loudly_without_a_device():
     with pytest.raises(error) as info:
         nls.solve_nls(1e-3, 0.1, 5, 1, np.ones(16), np.ones(23), np.ones(16) * 0.1)
     assert info.value.status > 0          # a cudaError_t: no CPU fallback exists
+
+
+def test_kernel_choice_and_stream_geometry_for_the_baseline_configs():
+    """nlsb_dev_rk4_2d_plan (host arithmetic): which 2D kernel the automatic path takes and how the strip-marching
+    kernel cuts the grid -- every SM busy, chunk rows + 6k a multiple of the unrolled march, strips covering the
+    columns."""
+    lib = _lib.load()
+
+    def plan(batch, n, order=5):
+        out = [C.c_int() for _ in range(4)]
+        assert lib.nlsb_dev_rk4_2d_plan(batch, n, n, order, *[C.byref(v) for v in out]) == 0
+        return [v.value for v in out]
+
+    assert plan(1, 512)[:2] == [1, 512]            # C2: one wave of 32x64 tiles
+    assert plan(1, 400)[0] in (0, 1) and plan(1, 256)[:2] == [0, 256] and plan(1, 768)[:2] == [0, 256]
+    assert plan(1, 513)[0] in (0, 1)               # odd widths never reach the strip-marching kernel
+    for batch, n, order in ((1, 8192, 5), (256, 1024, 5), (1, 2048, 5), (1, 4096, 3), (1, 4096, 7), (8, 1024, 5)):
+        kernel, threads, strips, chunk = plan(batch, n, order)
+        k = (order - 1) // 2
+        assert kernel == 2 and threads in (128, 192, 256)
+        assert strips * (threads - 8 * k) >= n > (strips - 1) * (threads - 8 * k)
+        assert (chunk + 6 * k) % (2 * (2 * k + 1)) == 0 and chunk >= 1
+        ctas = strips * -(-n // chunk) * batch
+        assert ctas >= 140                          # at least ~one CTA per SM
+    assert plan(256, 1024)[1] == 128                # C5 members: the two-CTAs-per-SM shape costs no extra columns
+    assert plan(1, 8192)[1:3] == [256, 35]
