@@ -179,8 +179,9 @@ def measured_hbm_peak():
 
 
 # ---- reference arm: the CPU oracle ------------------------------------------------------------------
-def cpu_sample(w, kind="sp", budget_points=1.3e7):
-    """Times the oracle on a bounded sample of workload `w`: one member, `s` RK steps."""
+def cpu_sample(w, kind="sp", budget_points=1.0e8):
+    """Times the oracle on a bounded sample of workload `w`: one member, `s` RK steps (about 10-25 s of CPU work
+    for the 2D workloads at the oracle's ~5-9e6 point-steps/s; a 1D member's whole horizon is shorter than that)."""
     from oracle import oracle as O
     k = O.sp if kind == "sp" else O.dp
     per_step = w["n"] if w["dim"] == 1 else w["n"] ** 2
@@ -379,7 +380,7 @@ def run_engine(args):
         if world == 1 and not args.no_cpu:
             wc = build_inputs(name, args.iters, 1 if spec["batch"] > 1 else None)
             rate, dt_cpu, sample = cpu_sample(wc, "sp")
-            rate_dp, _, sample_dp = cpu_sample(wc, "dp", budget_points=6.0e6)
+            rate_dp, _, sample_dp = cpu_sample(wc, "dp", budget_points=2.0e7)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                     "host_cores": os.cpu_count(), "dp_value": rate_dp, "dp_sample": sample_dp}
         print(json.dumps(line))
