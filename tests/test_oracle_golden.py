@@ -173,3 +173,46 @@ def test_chemical_potential_consistency():
     assert abs(mu - ref) <= 1e-12 * abs(ref)
     mus = O.sp.chemical_potential_1d(m.dx, P, c, u)
     assert abs(mus - ref) <= 1e-3 * abs(ref)
+
+
+def _dense_from_band(op):
+    """Dense matrix of a BLAS band (ku = kl = k): A(i, j) = op(k + i - j, j)."""
+    m, n = op.shape
+    k = (m - 1) // 2
+    A = np.zeros((n, n))
+    for j in range(n):
+        for b in range(m):
+            i = j + b - k
+            if 0 <= i < n:
+                A[i, j] = op[b, j]
+    return A
+
+
+@pytest.mark.parametrize("order", [3, 5, 7])
+def test_solver_level_second_opinion_1d(order):
+    """Nothing in the reference pins hamiltonian / runge_kutta / solve_nls ("parity unpinned").  A second,
+    independently written restatement -- dense numpy algebra straight from Appendix A.1 / A.5 (v = (a - i b) u +
+    i A u; classical RK4), sharing only the operator table -- must agree with the oracle's C code."""
+    n, dx, dt, iters = 60, 0.1, 1e-3, 40
+    rng = np.random.default_rng(order)
+    P = 10.0 * rng.random(n)
+    c = np.zeros(23)
+    c[[2, 3, 4, 5, 11, 12, 13]] = [1.0, 1.0, 1.0, 2.8, 0.13658959, 1.0, 0.74626866]
+    u = 0.1 + 0.05 * rng.standard_normal(n) + 0.05j * rng.standard_normal(n)
+    A = _dense_from_band(O.dp.make_laplacian(n, order, dx))
+
+    def rhs(y):
+        usq = np.abs(y) ** 2
+        res = c[11] * P / (c[12] + c[13] * usq)
+        return ((c[2] * res - c[3]) - 1j * (c[4] * usq + c[5] * res)) * y + 1j * (A @ y)
+
+    assert np.allclose(O.dp.hamiltonian(P, c, u, O.dp.make_laplacian(n, order, dx)), rhs(u), rtol=1e-13, atol=1e-13)
+    y = u.copy()
+    for _ in range(iters):
+        k1 = rhs(y)
+        k2 = rhs(y + k1 * dt / 2)
+        k3 = rhs(y + k2 * dt / 2)
+        k4 = rhs(y + k3 * dt)
+        y = y + (k1 + 2 * k2 + 2 * k3 + k4) * dt / 6
+    got = O.dp.solve_nls(dt, dx, order, iters, P, c, u)
+    assert np.linalg.norm(got - y) / np.linalg.norm(y) <= 1e-13
