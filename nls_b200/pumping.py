@@ -1,21 +1,25 @@
 """Pumping profiles P(x[, y]) sampled on the solver grid.
 
-Host-side mirror of the reference's ``nls/pumping.py`` (class names, constructor arguments,
-``setPower``, ``+``/``-`` combinators and call signatures are the reference's).  The profiles feed
-the hot path as the float64 array ``pumping`` of ``solve_nls*``; ``BASELINE.json`` asks for the
-sampled profile to be *bit-exact*, so every ``__call__`` below evaluates the same numpy expression
-tree, in the same association order, as the reference line it cites -- including the reference's
-quirks:
+Host-side counterpart of the reference's ``nls/pumping.py``: the same public names, constructor parameters,
+``setPower``, ``+`` / ``-`` combinators and call signatures, so that user scripts keep working.  The profiles feed
+the hot path as the float64 array ``pumping`` of ``solve_nls*``, and ``BASELINE.json`` asks for the sampled profile to
+be *bit-exact*: each formula below is therefore the numpy expression tree of the reference line it cites, in the same
+association order -- including the reference's quirks:
 
-* the base-class constructor drops its ``power`` argument (ref ``pumping.py:15-16``): combinators
-  always scale by 1.0 and ``GaussianElipticPumping2D`` ignores the ``power`` it is given;
+* the root constructor ignores the ``power`` it is given (ref ``pumping.py:15-16``): combinators always scale by
+  1.0 until ``setPower`` is called, and ``GaussianElipticPumping2D`` starts with amplitude 1.0;
 * a ring is the *sum* of two full-power Gaussians centred at +R and -R (ref ``:156-159``).
 
-Parity: ``tests/test_pumping.py`` compares against golden arrays produced by the reference module
-itself (``tests/golden/make_golden.py``).
+Organisation (this file's own): the formulas are module-level functions, leaf profiles declare their parameters in a
+``_signature`` table that one shared constructor binds, combinators carry the numpy operator they apply.
+
+Parity: ``tests/test_pumping.py`` compares against golden arrays produced by the reference module itself
+(``tests/golden/make_golden.py``).
 """
 
 from __future__ import annotations
+
+import operator
 
 import numpy as np
 
@@ -27,20 +31,42 @@ __all__ = [
 ]
 
 
+# ---- formulas (expression trees of the reference) ---------------------------------------------------------------
 def _gauss(power, dx, dy, variation):
-    # ref pumping.py:126 -- power * exp(-((x-x0)**2 + (y-y0)**2) / (2.0 * variation**2))
+    # ref pumping.py:126
     return power * np.exp(-(dx ** 2 + dy ** 2) / (2.0 * variation ** 2))
 
 
+def _radii(x, y, x0, y0):
+    # ref pumping.py:174
+    return np.sqrt((x - x0) ** 2 + (y - y0) ** 2)
+
+
+def _ellipse(power, x, y, x0, y0, var, a, b):
+    # ref pumping.py:194-199: width enters as 2 * var (not squared), polar radius measured from the grid origin
+    angle = np.arctan2(x - x0, y - y0)
+    re = np.sqrt((a * np.cos(angle)) ** 2 + (b * np.sin(angle)) ** 2)
+    rp = np.sqrt(x ** 2 + y ** 2)
+    return power * (np.exp(-(re - rp) ** 2 / (2 * var)) + np.exp(-(re + rp) ** 2 / (2 * var)))
+
+
+def _tophat(power, x, x0, width):
+    # ref pumping.py:213-217
+    lo, hi = x0 - width / 2.0, x0 + width / 2.0
+    out = np.zeros(x.shape)
+    out[(x >= lo) & (x <= hi)] = power
+    return out
+
+
+# ---- the tree ---------------------------------------------------------------------------------------------------
 class AbstractPumping(object):
     """Root of the pumping tree (ref ``pumping.py:11-40``)."""
 
     def __init__(self, power=1.0):
-        # ref :15-16 -- the argument is accepted and ignored; the local multiplier starts at 1.0
-        self.power = 1.0
+        self.power = 1.0            # ref :15-16 -- the argument is accepted and ignored
 
     def setPower(self, power):
-        """Local multiplier for combinators, physical power for leaf profiles (ref ``:18-22``)."""
+        """Local multiplier of a combinator, physical power of a leaf (ref ``:18-22``)."""
         self.power = power
 
     def __call__(self, *args, **kwargs):
@@ -53,46 +79,62 @@ class AbstractPumping(object):
         return OpSubPumping(self, other)
 
     def __repr__(self):
-        return "AbstractPumping"
+        return type(self).__name__ if type(self) is AbstractPumping else "<class %s(AbstractPumping)>" % type(self).__name__
 
-    __str__ = __repr__
+    def __str__(self):
+        return repr(self)
 
 
-class _BinaryPumping(AbstractPumping):
-    symbol = "?"
+class _Combination(AbstractPumping):
+    """``power * (lhs <op> rhs)`` with the local multiplier starting at 1.0."""
+    symbol, combine = "?", None
 
     def __init__(self, lhs, rhs):
         AbstractPumping.__init__(self)
         self.lhs, self.rhs = lhs, rhs
 
+    def __call__(self, *args, **kwargs):
+        if self.combine is None:
+            raise Exception("Not supported yet!")
+        return self.power * type(self).combine(self.lhs(*args, **kwargs), self.rhs(*args, **kwargs))
+
     def __repr__(self):
         return "%r %s %r" % (self.lhs, self.symbol, self.rhs)
 
-    __str__ = __repr__
+
+class OpSumPumping(_Combination):
+    """ref ``:43-57``"""
+    symbol, combine = "+", operator.add
 
 
-class OpSumPumping(_BinaryPumping):
-    """``power * (lhs + rhs)`` (ref ``:43-57``)."""
-    symbol = "+"
-
-    def __call__(self, *args, **kwargs):
-        return self.power * (self.lhs(*args, **kwargs) + self.rhs(*args, **kwargs))
+class OpSubPumping(_Combination):
+    """ref ``:60-74``"""
+    symbol, combine = "-", operator.sub
 
 
-class OpSubPumping(_BinaryPumping):
-    """``power * (lhs - rhs)`` (ref ``:60-74``)."""
-    symbol = "-"
-
-    def __call__(self, *args, **kwargs):
-        return self.power * (self.lhs(*args, **kwargs) - self.rhs(*args, **kwargs))
-
-
-class OpMulPumping(_BinaryPumping):
+class OpMulPumping(_Combination):
     """Cartesian product of two 1D profiles -- unsupported in the reference too (ref ``:77-92``)."""
     symbol = "x"
 
-    def __call__(self, *args, **kwargs):
-        raise Exception("Not supported yet!")
+
+class _Leaf(AbstractPumping):
+    """A profile with named parameters: ``_signature`` = ((constructor name, default, attribute or None), ...);
+    attribute None means the reference accepts the argument and drops it."""
+    _signature = ()
+
+    def __init__(self, *args, **kwargs):
+        AbstractPumping.__init__(self)
+        names = [entry[0] for entry in self._signature]
+        if len(args) > len(names):
+            raise TypeError("%s takes at most %d arguments" % (type(self).__name__, len(names)))
+        given = dict(zip(names, args))
+        for key, value in kwargs.items():
+            if key not in names or key in given:
+                raise TypeError("%s: unexpected or repeated argument %r" % (type(self).__name__, key))
+            given[key] = value
+        for name, default, attribute in self._signature:
+            if attribute is not None:
+                setattr(self, attribute, given.get(name, default))
 
 
 class GridPumping(AbstractPumping):
@@ -109,15 +151,10 @@ class GridPumping(AbstractPumping):
     def __repr__(self):
         return self.desciption
 
-    __str__ = __repr__
 
-
-class GaussianPumping(AbstractPumping):
+class GaussianPumping(_Leaf):
     """Gaussian spot with origin, peak power and width (ref ``:113-131``)."""
-
-    def __init__(self, power=1.0, x0=0.0, y0=0.0, variation=5.0):
-        AbstractPumping.__init__(self)
-        self.power, self.x0, self.y0, self.variation = power, x0, y0, variation
+    _signature = (("power", 1.0, "power"), ("x0", 0.0, "x0"), ("y0", 0.0, "y0"), ("variation", 5.0, "variation"))
 
     def __call__(self, x, y, t=None):
         return _gauss(self.power, x - self.x0, y - self.y0, self.variation)
@@ -125,8 +162,6 @@ class GaussianPumping(AbstractPumping):
     def __repr__(self):
         return "{0} exp(-{1} ((x - {2})^2 - (y - {3})^2))".format(
             self.power, 1.0 / (2.0 * self.variation ** 2), self.x0, self.y0)
-
-    __str__ = __repr__
 
 
 class GaussianPumping1D(GaussianPumping):
@@ -137,85 +172,55 @@ class GaussianPumping1D(GaussianPumping):
 
 
 class GaussianPumping2D(GaussianPumping):
-    """Alias of :class:`GaussianPumping` for the 2D model (ref ``:145-150``)."""
+    """The same spot under its 2D name (ref ``:145-150``)."""
 
 
 class GaussianRingPumping1D(OpSumPumping):
     """Ring of radius R in the radial model: G(x; +R) + G(x; -R) (ref ``:152-160``)."""
 
     def __init__(self, power=1.0, radius=0.0, variation=5.0):
-        OpSumPumping.__init__(self,
-                              GaussianPumping1D(power, +radius, 0.0, variation),
-                              GaussianPumping1D(power, -radius, 0.0, variation))
+        halves = [GaussianPumping1D(power, centre, 0.0, variation) for centre in (+radius, -radius)]
+        OpSumPumping.__init__(self, *halves)
 
 
-class GaussianRingPumping2D(AbstractPumping):
+class GaussianRingPumping2D(_Leaf):
     """Ring with arbitrary centre on the Cartesian grid (ref ``:163-178``)."""
+    _signature = (("power", 1.0, None), ("x0", 0.0, "x0"), ("y0", 0.0, "y0"), ("variation", 5.0, None),
+                  ("radius", 1.0, None))
 
     def __init__(self, power=1.0, x0=0.0, y0=0.0, variation=5.0, radius=1.0):
-        AbstractPumping.__init__(self)
-        self.x0, self.y0 = x0, y0
+        _Leaf.__init__(self, power, x0, y0, variation, radius)
         self.pumping = GaussianRingPumping1D(power, radius, variation)
 
     def __call__(self, x, y, t=None):
-        radii = np.sqrt((x - self.x0) ** 2 + (y - self.y0) ** 2)
-        return self.pumping(radii, t)
-
-    def __repr__(self):
-        return "<class GaussianRingPumping2D(AbstractPumping)>"
-
-    __str__ = __repr__
+        return self.pumping(_radii(x, y, self.x0, self.y0), t)
 
 
-class GaussianElipticPumping2D(AbstractPumping):
-    """Ring replaced by an ellipse with semi-axes a, b (ref ``:181-202``).
-
-    Note the reference's own arithmetic: the width enters as ``2 * var`` (not squared), the polar
-    radius is measured from the grid origin (not from ``x0, y0``), and ``power`` is dropped by the
-    base constructor, so the amplitude is 1.0 until ``setPower`` is called.
-    """
-
-    def __init__(self, power=1.0, x0=0.0, y0=0.0, variation=5.0, a=1.0, b=1.0):
-        AbstractPumping.__init__(self, power)
-        self.x0, self.y0, self.var, self.a, self.b = x0, y0, variation, a, b
+class GaussianElipticPumping2D(_Leaf):
+    """Ring replaced by an ellipse with semi-axes a, b (ref ``:181-202``); the ``power`` argument is dropped by the
+    root constructor, so the amplitude is 1.0 until ``setPower`` is called."""
+    _signature = (("power", 1.0, None), ("x0", 0.0, "x0"), ("y0", 0.0, "y0"), ("variation", 5.0, "var"),
+                  ("a", 1.0, "a"), ("b", 1.0, "b"))
 
     def __call__(self, x, y, t=None):
-        t = np.arctan2(x - self.x0, y - self.y0)
-        re = np.sqrt((self.a * np.cos(t)) ** 2 + (self.b * np.sin(t)) ** 2)
-        rp = np.sqrt(x ** 2 + y ** 2)
-        return self.power * (np.exp(-(re - rp) ** 2 / (2 * self.var)) +
-                             np.exp(-(re + rp) ** 2 / (2 * self.var)))
-
-    def __repr__(self):
-        return "<class GaussianElipticPumping2D(AbstractPumping)>"
-
-    __str__ = __repr__
+        return _ellipse(self.power, x, y, self.x0, self.y0, self.var, self.a, self.b)
 
 
-class RectangularPumping1D(AbstractPumping):
+class RectangularPumping1D(_Leaf):
     """Top-hat of given width centred at x0 (ref ``:205-220``)."""
-
-    def __init__(self, power=10.0, x0=0.0, width=1.0):
-        AbstractPumping.__init__(self, power)
-        self.x0, self.width, self.power = x0, width, power
+    _signature = (("power", 10.0, "power"), ("x0", 0.0, "x0"), ("width", 1.0, "width"))
 
     def __call__(self, x, t=None):
-        lo, hi = self.x0 - self.width / 2.0, self.x0 + self.width / 2.0
-        out = np.zeros(x.shape)
-        out[(x >= lo) & (x <= hi)] = self.power
-        return out
+        return _tophat(self.power, x, self.x0, self.width)
 
     def __repr__(self):
         return "{0} * (\\theta(x - {1}) - \\theta({2} - x))".format(
             self.power, self.x0 + self.width / 2.0, self.x0 - self.width / 2.0)
-
-    __str__ = __repr__
 
 
 class RectangularRingPumping1D(OpSumPumping):
     """Two top-hats at +R and -R (ref ``:223-229``)."""
 
     def __init__(self, power=10.0, radius=10.0, width=2.0):
-        OpSumPumping.__init__(self,
-                              RectangularPumping1D(power, +radius, width),
-                              RectangularPumping1D(power, -radius, width))
+        halves = [RectangularPumping1D(power, centre, width) for centre in (+radius, -radius)]
+        OpSumPumping.__init__(self, *halves)
