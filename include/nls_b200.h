@@ -166,6 +166,11 @@ size_t nlsb_dev_rk4_2d_workspace(int batch, int rows, int cols);
  * with per-stage edge exchange through L2 (experimental, slower; falls back to 4 when the grid does not
  * fit).  All give the same result to rounding (2..9 bitwise); the switch exists for tests and profiling. */
 int nlsb_set_2d_path(int path);
+/* Tuning of the strip-marching kernel (tests, profiling): sync = how the threads of a CTA order their shared-memory
+ * traffic (0 one barrier per row, 1 one barrier per two rows; -1 = library default),
+ * width = threads per strip (one of the compiled widths; 0 = automatic), iters_per_cta = rows a CTA marches
+ * (0 = automatic).  Every setting produces the same bits. */
+int nlsb_set_stream_tuning(int sync, int width, int iters_per_cta);
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
                     const double *wy, const double *pumping, const double *coeffs,
                     const double *shared_coeffs_host, double *psi,
@@ -230,6 +235,36 @@ int nlsb_dev_diagnostics_2d(int batch, int rows, int cols, int order, double dx,
  * Grid and arithmetic are bit-identical to numpy's, exp() may differ in the last place (<= 4 ulp in the result). */
 int nlsb_dev_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_host,
                               double *out, nlsb_stream_t stream);
+
+/* ---- multi-GPU row slabs: peer-mapped buffers and the device-initiated halo exchange -----------------------
+ * The reference has no parallelism; BASELINE.json config 4 asks for the 8192^2 grid cut into row
+ * slabs over the GPUs of one box (nls_b200/multigpu.py).  One process per GPU.
+ * nlsb_peer_alloc: zero-filled device memory whose allocation can be exported (cudaMalloc + cudaIpcGetMemHandle);
+ * nlsb_peer_export writes the 64-byte IPC handle, nlsb_peer_open maps another process's allocation into this one
+ * (peer access over NVLink is enabled on first use), nlsb_peer_close unmaps it. */
+int nlsb_peer_alloc(size_t bytes, void **ptr);
+int nlsb_peer_free(void *ptr);
+int nlsb_peer_export(const void *ptr, unsigned char *handle64);
+int nlsb_peer_open(const unsigned char *handle64, void **ptr);
+int nlsb_peer_close(void *ptr);
+int nlsb_peer_enable_access(int peer_device);
+/* One halo exchange of a slab, enqueued as ONE kernel on `stream`, no host work (capturable in a CUDA graph):
+ * the kernel tells both neighbours that this rank's halo rows may be overwritten, waits for the same word from
+ * them, copies `complex_count` complex128 values from src_up / src_down (this rank's boundary rows) to dst_up /
+ * dst_down (the neighbours' halo rows, peer-mapped pointers), publishes "data of epoch e" in the neighbours' flag
+ * blocks and returns when the neighbours' data of the same epoch has arrived in this rank's halo rows.
+ * state: 64 zero-initialised bytes of this rank's memory (epoch counter, ticket, time-out count);
+ * flags_mine: this rank's flag block (256 zero-initialised bytes from nlsb_peer_alloc); flags_up / flags_down: the
+ * neighbours' flag blocks (peer-mapped) or NULL at the ends of the chain.  A wait gives up after timeout_seconds
+ * (<= 0: 2 s) and is then counted in the state block (nlsb_dev_halo_status) instead of hanging the device. */
+int nlsb_dev_halo_exchange(const double *src_up, double *dst_up, const double *src_down, double *dst_down,
+                           size_t complex_count, void *state, void *flags_mine, void *flags_up, void *flags_down,
+                           double timeout_seconds, nlsb_stream_t stream);
+/* Synchronous read-back of a state block: exchanges completed and waits that timed out. */
+int nlsb_dev_halo_status(const void *state, unsigned long long *epoch, unsigned long long *timeouts);
+/* Adds to the count reported by nlsb_kernel_launches(): kernels replayed from a CUDA graph the CALLER captured
+ * are launched without passing through the library. */
+void nlsb_add_kernel_launches(unsigned long long n);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "nlsb_dev_band_matvec_1d": (_I, [_I, _I, _P, _P, _P, _F, _P]),
     "nlsb_dev_rk4_2d_workspace": (_Z, [_I, _I, _I]),
     "nlsb_set_2d_path": (_I, [_I]),
+    "nlsb_set_stream_tuning": (_I, [_I, _I, _I]),
     "nlsb_dev_rk4_2d": (_I, [_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "nlsb_dev_rk4_step_2d_slab": (_I, [_I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "nlsb_planar_pitch": (_I, [_I]),
@@ -68,6 +69,15 @@ PROTOTYPES = {
     "nlsb_dev_reservoir": (_I, [_Z, _P, _P, _P, _P, _P]),
     "nlsb_dev_rk4_2d_plan": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "nlsb_dev_pumping_profiles": (_I, [_I, _I, _I, _I, _F, _P, _P, _P]),
+    "nlsb_peer_alloc": (_I, [_Z, _P]),
+    "nlsb_peer_free": (_I, [_P]),
+    "nlsb_peer_export": (_I, [_P, _P]),
+    "nlsb_peer_open": (_I, [_P, _P]),
+    "nlsb_peer_close": (_I, [_P]),
+    "nlsb_peer_enable_access": (_I, [_I]),
+    "nlsb_dev_halo_exchange": (_I, [_P, _P, _P, _P, _Z, _P, _P, _P, _P, _F, _P]),
+    "nlsb_dev_halo_status": (_I, [_P, _P, _P]),
+    "nlsb_add_kernel_launches": (None, [C.c_ulonglong]),
     "nlsb_dev_diagnostics_scratch": (_Z, [_I]),
     "nlsb_dev_diagnostics_1d": (_I, [_I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "nlsb_dev_diagnostics_2d": (_I, [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -538,6 +538,14 @@ int nlsb_set_2d_path(int path)
     return 0;
 }
 
+int nlsb_set_stream_tuning(int sync, int width, int iters_per_cta)
+{
+    if (sync < -1 || sync > 1 || width < 0 || iters_per_cta < 0)
+        return fail(NLSB_EINVAL, "stream tuning: sync in -1..1, width and iterations >= 0 (0 = automatic)");
+    stream_2d_set_tuning(sync, width, iters_per_cta);
+    return 0;
+}
+
 int nlsb_device_available(void)
 {
     int count = 0;

@@ -56,6 +56,7 @@ int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const
 // and writes interleaved psi (grids with an odd number of columns are handed to the tile kernel: same bits).
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
 int stream_2d_plan(int order, int batch, int out_rows, int cols, int *threads, int *strips, int *chunk_rows);
+void stream_2d_set_tuning(int sync, int width, int iters);
 // resident_2d.cu: `steps` RK4 steps of a SMALL grid in one cooperative launch, psi updated in place; the field
 // lives in registers (one patch per CTA), neighbouring CTAs exchange edge nodes through `mailbox` (device scratch
 // of the size resident_2d_query reports, zero-filled before its first use).  Packets carry sequence numbers

@@ -17,6 +17,7 @@
 #include "stream_2d_core.cuh"
 
 #include <cuda.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,17 @@ namespace nlsb {
 namespace {
 
 using namespace stream2d;
+
+// Tuning knobs (nlsb_set_stream_tuning; initial values from NLSB_STREAM_SYNC / NLSB_STREAM_T / NLSB_STREAM_ITERS):
+// -1 / 0 = the library's own choice.
+int env_int(const char *name, int fallback)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : fallback;
+}
+std::atomic<int> g_tune_sync{env_int("NLSB_STREAM_SYNC", -1)};
+std::atomic<int> g_tune_width{env_int("NLSB_STREAM_T", 0)};
+std::atomic<int> g_tune_iters{env_int("NLSB_STREAM_ITERS", 0)};
 
 struct StreamArgs {
     int rows, cols;          // extent of the local arrays
@@ -80,12 +92,25 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *map, uint3
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-template <typename C, bool UNIFORM>
+// How often the threads of a CTA meet.  A stage-ring row written in iteration `it` is read in it + K and overwritten
+// in it + 2K + 1, so ONE __syncthreads per min(K, 2) iterations is enough: the barrier after every second iteration
+// still separates each write from its read K >= 2 iterations later and each read from the overwrite K + 1 later.
+//   kSyncEvery  a barrier per iteration (round 1)
+//   kSyncPair   a barrier per two iterations when K >= 2
+// Measured on B200 (profiles/r2_stream_sync_sweep.jsonl, order 5): the pair flavour is 1-3 % faster with two
+// 128-thread CTAs per SM and 1 % slower with one 256-thread CTA.  Two further flavours were measured and removed:
+// split-phase mbarriers (warps arrive after iteration it, wait for the arrivals of it - K: 6-19 % SLOWER -- the
+// TRYWAIT round trip per iteration costs more than the drift buys) and one barrier between stage 1 and stages
+// 2-4 (9-14 % slower: the stage 2-4 loads can then no longer be hoisted above the stage-1 arithmetic).
+enum StreamSync { kSyncEvery = 0, kSyncPair = 1 };
+
+template <typename C, bool UNIFORM, int SYNC>
 __global__ void __launch_bounds__(C::T, C::CTAS_PER_SM)
 rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ StreamWeights<C::K> wa,
                   const __grid_constant__ TensorMap map, const __grid_constant__ TensorMap map_p)
 {
     constexpr int K = C::K, U = C::U, RB = C::RB, NB = C::NB;
+    constexpr int PERIOD = (SYNC == kSyncPair && K >= 2) ? 2 : 1;     // iterations per __syncthreads (U is even)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *yr = reinterpret_cast<double2 *>(smem_raw);
     double2 *ring = reinterpret_cast<double2 *>(smem_raw + C::RING_OFFSET);
@@ -135,11 +160,18 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
                 mbar_wait(bar0 + 8 * (b % NB), (b / NB) & 1);
             }
             march_iter<C>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_);
-            __syncthreads();
-            if ((ph + K + 1) % RB == 0 && tid == 0) {   // every row of batch (it + K + 1) / RB - 1 has been consumed
-                const int nb = (it + K + 1) / RB - 1 + NB;
+            if ((ph + 1) % PERIOD == 0) {
+                __syncthreads();
+                // thread 0 re-requests the batches whose last reader was one of the iterations this barrier closes:
+                // iteration x is the last reader of batch (x + K + 1) / RB - 1 when (x + K + 1) % RB == 0.
                 // WAR across proxies (generic reads, then the TMA write) is ordered by the barrier above
-                if (nb < g.nbatches) issue(nb);
+#pragma unroll
+                for (int back = PERIOD - 1; back >= 0; --back) {
+                    if ((ph - back + K + 1) % RB == 0 && tid == 0) {
+                        const int nb = (it - back + K + 1) / RB - 1 + NB;
+                        if (nb < g.nbatches) issue(nb);
+                    }
+                }
             }
         }
         const double2 *t = rh; rh = ro; ro = t;
@@ -221,7 +253,7 @@ int cached_map(const MapKey &key, TensorMap *out)
     return 0;
 }
 
-template <typename C, bool UNIFORM>
+template <typename C, bool UNIFORM, int SYNC>
 int configure_stream()
 {
     static bool configured[64] = {};
@@ -229,9 +261,9 @@ int configure_stream()
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
@@ -251,48 +283,65 @@ int sm_count()
     return sms[dev];
 }
 
-// Rows per chunk.  One CTA per SM runs at a time, every CTA of m U iterations spends 6K of them filling and
-// draining the stage pipeline (plus a fixed prologue worth about 8): pick the m that minimises
-// waves x (iterations per CTA), i.e. long chunks, but not so long that the last wave is mostly empty.
-template <typename C>
-int chunk_rows_for(int out_rows, int strips, int batch)
+// Launch geometry: strip width T (threads per CTA), strips, rows per chunk.
+// * A strip of T threads produces W = T - 8K columns, so `cols` columns sweep ceil(cols / W) * T frame columns.
+// * Every CTA of m U iterations spends 6K of them filling and draining the stage pipeline (plus a fixed prologue
+//   worth about 8), and CTAs run in waves of (SMs x CTAs per SM).
+// The planner minimises   waves x (iterations per CTA + 8) x (time of one iteration of a full SM)   over the
+// compiled widths and the chunk lengths.  The time of an iteration of a full SM is T x CTAs-per-SM x shape_cost(T):
+// two 128-thread CTAs per SM overlap each other's load bursts and barriers and need 8.5 % less time per thread than
+// one 256-thread CTA (measured on B200, order 5, 8192^2 and 32 x 1024^2, profiles/r2_stream_sync_sweep.jsonl;
+// 160 / 192 / 224-thread strips were measured too and dropped: a CTA whose warps do not divide evenly over the four
+// schedulers runs at the pace of the fullest one -- 224 threads take as long per iteration as 256).
+struct StreamPlan {
+    int threads, strips, chunk_rows, sync;
+    double cost;
+};
+
+inline double shape_cost(int K, int T)
 {
-    static const int forced = [] {
-        const char *e = std::getenv("NLSB_STREAM_ITERS");     // tuning knob: iterations per CTA
-        return e ? std::atoi(e) : 0;
-    }();
-    if (forced >= 6 * C::K + C::U) return C::chunk_rows(forced);
-    const long long sms = (long long)sm_count() * C::CTAS_PER_SM;      // CTAs resident at once
-    int best_h = C::chunk_rows(140);
-    double best_cost = 0.0;
-    for (int m = (6 * C::K) / C::U + 2; m <= 96; ++m) {
+    if (K == 2 && T == 128) return 0.915;
+    if (K == 1 && T == 128) return 1.03;
+    return 1.0;
+}
+
+template <typename C>
+StreamPlan plan_shape(int out_rows, int cols, int batch)
+{
+    StreamPlan p{C::T, (cols + C::W - 1) / C::W, C::chunk_rows(140), kSyncEvery, 0.0};
+    p.sync = (C::T <= 128 && C::K >= 2) ? kSyncPair : kSyncEvery;
+    const double per_iter = (double)C::T * C::CTAS_PER_SM * shape_cost(C::K, C::T);
+    const long long slots = (long long)sm_count() * C::CTAS_PER_SM;      // CTAs resident at once
+    const int forced = g_tune_iters.load();                              // tuning knob: iterations per CTA
+    const int m_lo = forced >= 6 * C::K + C::U ? (forced + C::U - 1) / C::U : (6 * C::K) / C::U + 2;
+    const int m_hi = forced >= 6 * C::K + C::U ? m_lo : 96;
+    for (int m = m_lo; m <= m_hi; ++m) {
         const int h = m * C::U - 6 * C::K;
-        const long long ctas = (long long)strips * ((out_rows + h - 1) / h) * batch;
-        const long long waves = (ctas + sms - 1) / sms;
+        const long long ctas = (long long)p.strips * ((out_rows + h - 1) / h) * batch;
+        const long long waves = (ctas + slots - 1) / slots;
         const int last = out_rows - (out_rows - 1) / h * h;            // rows of the last chunk
         const int iters = out_rows > h ? m * C::U : (last + 6 * C::K + C::U - 1) / C::U * C::U;
-        const double cost = (double)waves * (iters + 8);
-        if (best_cost == 0.0 || cost <= best_cost) {
-            best_cost = cost;
-            best_h = h;
+        const double cost = (double)waves * (iters + 8) * per_iter;
+        if (p.cost == 0.0 || cost <= p.cost) {
+            p.cost = cost;
+            p.chunk_rows = h;
         }
         if (out_rows <= h) break;
     }
-    return best_h;
+    return p;
 }
 
-template <typename C, bool UNIFORM>
-int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+template <typename C, bool UNIFORM, int SYNC>
+int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
-    int rc = configure_stream<C, UNIFORM>();
+    int rc = configure_stream<C, UNIFORM, SYNC>();
     if (rc) return rc;
     const int out_rows = s.out_row1 - s.out_row0;
-    if (out_rows <= 0 || s.cols <= 0 || s.batch <= 0) return 0;
     StreamArgs a{};
     a.rows = s.rows; a.cols = s.cols; a.grow0 = s.grow0; a.grows = s.grows;
     a.out_row0 = s.out_row0; a.out_row1 = s.out_row1;
-    a.strips = (s.cols + C::W - 1) / C::W;
-    a.chunk_rows = chunk_rows_for<C>(out_rows, a.strips, s.batch);
+    a.strips = p.strips;
+    a.chunk_rows = p.chunk_rows;
     a.out = s.out; a.coeffs = s.coeffs;
     if (UNIFORM) a.cu = *s.uniform;
     a.dt = s.dt;
@@ -305,66 +354,83 @@ int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, cudaStream_t 
     if (rc) return rc;
     const int chunks = (out_rows + a.chunk_rows - 1) / a.chunk_rows;
     const dim3 grid((unsigned)(a.strips * chunks), (unsigned)s.batch);
-    rk4_stream_kernel<C, UNIFORM><<<grid, C::T, C::SMEM, stream>>>(a, wa, map, map_p);
+    rk4_stream_kernel<C, UNIFORM, SYNC><<<grid, C::T, C::SMEM, stream>>>(a, wa, map, map_p);
     count_launches(1);
     return (int)cudaGetLastError();
 }
 
-template <int K>
-struct StreamShape {
-    using Wide = Cfg<K, (K == 3) ? 192 : 256>;      // order 7: the rings of 256 columns do not fit in shared memory
-    using Narrow = Cfg<K, 128>;                     // two CTAs per SM: their barriers and load bursts are independent
-};
-
-// Two 128-thread CTAs per SM overlap each other's load bursts and barriers (+3 % per unit of work, measured) but
-// sweep T / W = 128 / 112 columns per useful column instead of 256 / 240: taken where that costs nothing
-// (1024-wide ensemble members: 10 x 128 = 5 x 256 columns).
-template <int K>
-bool narrow_shape(int cols)
+template <typename C>
+int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
-    using C = typename StreamShape<K>::Wide;
-    using N = typename StreamShape<K>::Narrow;
-    static const int force = [] {
-        const char *e = std::getenv("NLSB_STREAM_T");         // tuning knob: 128 or 256
-        return e ? std::atoi(e) : 0;
-    }();
-    const long long narrow = (long long)((cols + N::W - 1) / N::W) * N::T, wide = (long long)((cols + C::W - 1) / C::W) * C::T;
-    return force == 128 || (force == 0 && K != 3 && narrow <= wide);
+    if (p.sync == kSyncPair)
+        return s.uniform ? launch_stream_sync<C, true, kSyncPair>(s, w, p, stream) : launch_stream_sync<C, false, kSyncPair>(s, w, p, stream);
+    return s.uniform ? launch_stream_sync<C, true, kSyncEvery>(s, w, p, stream) : launch_stream_sync<C, false, kSyncEvery>(s, w, p, stream);
 }
 
-template <int K>
-int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
-{
-    using C = typename StreamShape<K>::Wide;
-    using N = typename StreamShape<K>::Narrow;
-    if (narrow_shape<K>(s.cols))
-        return s.uniform ? launch_stream_cfg<N, true>(s, w, stream) : launch_stream_cfg<N, false>(s, w, stream);
-    return s.uniform ? launch_stream_cfg<C, true>(s, w, stream) : launch_stream_cfg<C, false>(s, w, stream);
-}
+// Strip widths the march is compiled for (order 7 has one: rings of 256 columns exceed 227 KB of shared memory and
+// two 128-column CTAs do not fit one SM either).
+template <int K> struct StreamWidths;
+template <> struct StreamWidths<1> { static constexpr int n = 2; static constexpr int t[2] = {128, 256}; };
+template <> struct StreamWidths<2> { static constexpr int n = 2; static constexpr int t[2] = {128, 256}; };
+template <> struct StreamWidths<3> { static constexpr int n = 1; static constexpr int t[1] = {192}; };
 
-template <int K>
-void plan_k(int batch, int out_rows, int cols, int *threads, int *strips, int *chunk_rows)
+// Best plan over the compiled widths (or the forced one); ties go to the wider strip.
+template <int K, int I = 0>
+StreamPlan plan_stream(int batch, int out_rows, int cols)
 {
-    using C = typename StreamShape<K>::Wide;
-    using N = typename StreamShape<K>::Narrow;
-    if (narrow_shape<K>(cols)) {
-        *threads = N::T; *strips = (cols + N::W - 1) / N::W; *chunk_rows = chunk_rows_for<N>(out_rows, *strips, batch);
-    } else {
-        *threads = C::T; *strips = (cols + C::W - 1) / C::W; *chunk_rows = chunk_rows_for<C>(out_rows, *strips, batch);
+    using SW = StreamWidths<K>;
+    StreamPlan p = plan_shape<Cfg<K, SW::t[I]>>(out_rows, cols, batch);
+    const int force_t = g_tune_width.load(), force_sync = g_tune_sync.load();
+    if (force_sync == kSyncEvery || force_sync == kSyncPair) p.sync = force_sync;
+    if constexpr (I + 1 < SW::n) {
+        const StreamPlan q = plan_stream<K, I + 1>(batch, out_rows, cols);
+        if (force_t == p.threads) return p;
+        if (force_t == q.threads || q.cost <= p.cost) return q;
     }
+    return p;
+}
+
+template <int K, int I = 0>
+int launch_stream_k(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
+{
+    using SW = StreamWidths<K>;
+    if constexpr (I < SW::n) {
+        if (p.threads == SW::t[I]) return launch_stream_cfg<Cfg<K, SW::t[I]>>(s, w, p, stream);
+        return launch_stream_k<K, I + 1>(s, w, p, stream);
+    } else {
+        return fail(NLSB_EINVAL, "strip width %d is not compiled for order %d", p.threads, 2 * K + 1);
+    }
+}
+
+template <int K>
+int launch_stream_order(const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
+{
+    const int out_rows = s.out_row1 - s.out_row0;
+    if (out_rows <= 0 || s.cols <= 0 || s.batch <= 0) return 0;
+    return launch_stream_k<K>(s, w, plan_stream<K>(s.batch, out_rows, s.cols), stream);
 }
 
 }  // namespace
 
+void stream_2d_set_tuning(int sync, int width, int iters)
+{
+    g_tune_sync.store(sync);
+    g_tune_width.store(width);
+    g_tune_iters.store(iters);
+}
+
 // The launch geometry launch_rk4_step_stream_2d would use (host arithmetic only; needs no device).
 int stream_2d_plan(int order, int batch, int out_rows, int cols, int *threads, int *strips, int *chunk_rows)
 {
+    StreamPlan p;
     switch (order) {
-    case 3: plan_k<1>(batch, out_rows, cols, threads, strips, chunk_rows); return 0;
-    case 5: plan_k<2>(batch, out_rows, cols, threads, strips, chunk_rows); return 0;
-    case 7: plan_k<3>(batch, out_rows, cols, threads, strips, chunk_rows); return 0;
+    case 3: p = plan_stream<1>(batch, out_rows, cols); break;
+    case 5: p = plan_stream<2>(batch, out_rows, cols); break;
+    case 7: p = plan_stream<3>(batch, out_rows, cols); break;
+    default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
     }
-    return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+    *threads = p.threads; *strips = p.strips; *chunk_rows = p.chunk_rows;
+    return 0;
 }
 
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
@@ -374,9 +440,9 @@ int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeight
     // the pumping's tensor map needs a 16-byte row stride and base: other grids take the tile kernel (same bits)
     if ((s.cols & 1) || (reinterpret_cast<uintptr_t>(s.pumping) & 15) != 0) return launch_rk4_step_fused_2d(order, 0, s, w, stream);
     switch (order) {
-    case 3: return launch_stream_k<1>(s, w, stream);
-    case 5: return launch_stream_k<2>(s, w, stream);
-    case 7: return launch_stream_k<3>(s, w, stream);
+    case 3: return launch_stream_order<1>(s, w, stream);
+    case 5: return launch_stream_order<2>(s, w, stream);
+    case 7: return launch_stream_order<3>(s, w, stream);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
 }

@@ -59,7 +59,7 @@ struct Cfg {
     static constexpr size_t PRING_OFFSET = RING_OFFSET + RING_BYTES;
     static constexpr size_t PRING_BYTES = sizeof(double) * RING * T_;
     static constexpr size_t BAR_OFFSET = PRING_OFFSET + PRING_BYTES;
-    static constexpr size_t SMEM = BAR_OFFSET + 8 * NB + 64;
+    static constexpr size_t SMEM = BAR_OFFSET + 8 * (NB + NW) + 64;   // NB batch barriers + NW split-phase barriers
     static_assert(RING == 2 * U, "psi ring = two unrolled march bodies");
     static_assert(RB >= 2 * K_, "the first TMA batch must hold the 2K rows the march starts from");
     static_assert((sizeof(double) * RB * T_) % 128 == 0, "TMA batches must stay 128-byte aligned");

@@ -15,6 +15,12 @@ The arithmetic of a node does not depend on the partition (the kernel treats row
 as zero and every node follows the same sequence of roundings), so 1/2/4/8-rank results are bitwise
 identical -- ``tests/test_multigpu_cpu.py`` and ``tests/test_gpu_slabs.py`` check exactly that.
 
+On GPUs the halo exchange is DEVICE-INITIATED by default (``exchange="peer"``): the psi buffers are peer-mapped
+between neighbouring ranks (CUDA IPC over NVLink, ``csrc/peer.cu``), an exchange is one kernel that stores the
+boundary rows straight into the neighbours' halo rows and synchronises with them through flags in device memory,
+and the cycle "m RK4 steps + exchange" is captured in a CUDA graph -- no host work and no NCCL call on the data
+path.  ``exchange="nccl"`` keeps the host-issued grouped isend/irecv (the fallback when peer mapping is refused).
+
 One process per GPU; launch with ``torchrun`` (RANK / LOCAL_RANK / WORLD_SIZE from the environment).
 """
 
@@ -26,7 +32,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "halo_rows", "SlabPlan", "SlabGrid2D", "advance_emulated"]
+__all__ = ["shard_range", "halo_rows", "SlabPlan", "SlabGrid2D", "advance_emulated", "advance_emulated_peer", "link_local_peers"]
 
 STRIP_ROWS = 32   # boundary strips are one tile row of the fused kernel
 
@@ -166,6 +172,112 @@ def _default_cuda_stepper(plan, cols, dx, dt, order, coeffs):
     return _cuda_stepper(plan, cols, dx, dt, order, coeffs)
 
 
+class _DeviceArray(object):
+    """A device allocation the library owns, presented to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr = int(ptr)
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (self.ptr, False), "version": 2}
+
+
+class _PeerSlab(object):
+    """The peer-mapped memory of one slab: two psi buffers and a flag block from ``nlsb_peer_alloc`` (exportable
+    allocations), a private state block, and -- once ``connect`` ran -- the mapped pointers of both neighbours."""
+
+    FLAG_BYTES, STATE_BYTES = 256, 64
+
+    def __init__(self, plan, cols, device):
+        from . import _lib
+        self.plan, self.cols, self.device = plan, int(cols), device
+        self.row_bytes = 16 * self.cols
+        self.psi_bytes = self.row_bytes * plan.rows_alloc
+        self._own, self._mapped = [], []
+        with torch.cuda.device(device):
+            self.psi_ptr = [self._alloc(self.psi_bytes), self._alloc(self.psi_bytes)]
+            self.flags_ptr = self._alloc(self.FLAG_BYTES)
+            self.state_ptr = self._alloc(self.STATE_BYTES)
+        self.psi = [torch.as_tensor(_DeviceArray(p, (plan.rows_alloc, self.cols), "<c16"), device=device) for p in self.psi_ptr]
+        self.up_psi = self.down_psi = (None, None)
+        self.up_flags = self.down_flags = None
+        self._lib = _lib
+
+    def _alloc(self, nbytes):
+        from . import _lib
+        out = C.c_void_p()
+        _lib.call("nlsb_peer_alloc", C.c_size_t(nbytes), C.byref(out))
+        self._own.append(out.value)
+        return out.value
+
+    def handles(self):
+        """IPC handles of (psi buffer 0, psi buffer 1, flag block) as bytes."""
+        out = []
+        for ptr in (self.psi_ptr[0], self.psi_ptr[1], self.flags_ptr):
+            h = (C.c_ubyte * 64)()
+            self._lib.call("nlsb_peer_export", C.c_void_p(ptr), h)
+            out.append(bytes(h))
+        return out
+
+    def _open(self, handle):
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        self._lib.call("nlsb_peer_open", h, C.byref(out))
+        self._mapped.append(out.value)
+        return out.value
+
+    def connect(self, up_handles, down_handles):
+        with torch.cuda.device(self.device):
+            if up_handles is not None:
+                self.up_psi = (self._open(up_handles[0]), self._open(up_handles[1]))
+                self.up_flags = self._open(up_handles[2])
+            if down_handles is not None:
+                self.down_psi = (self._open(down_handles[0]), self._open(down_handles[1]))
+                self.down_flags = self._open(down_handles[2])
+
+    def connect_local(self, up, down):
+        """Neighbours living in the same process (single-GPU emulation of several ranks): plain pointers."""
+        if up is not None:
+            self.up_psi, self.up_flags = tuple(up.psi_ptr), up.flags_ptr
+        if down is not None:
+            self.down_psi, self.down_flags = tuple(down.psi_ptr), down.flags_ptr
+
+    def exchange(self, buf, timeout_seconds=5.0):
+        """Enqueue the halo exchange of psi buffer `buf` (0 / 1) on the current stream."""
+        p, rb = self.plan, self.row_bytes
+        a_up, _ = p.send_up()
+        a_dn, _ = p.send_down()
+        up_plan = SlabPlan(p.n, p.order, p.rank - 1, p.world, p.halo_steps) if p.up is not None else None
+        dn_plan = SlabPlan(p.n, p.order, p.rank + 1, p.world, p.halo_steps) if p.down is not None else None
+        null = C.c_void_p(None)
+        self._lib.call(
+            "nlsb_dev_halo_exchange",
+            C.c_void_p(self.psi_ptr[buf] + a_up * rb) if up_plan else null,
+            C.c_void_p(self.up_psi[buf] + up_plan.recv_from_down()[0] * rb) if up_plan else null,
+            C.c_void_p(self.psi_ptr[buf] + a_dn * rb) if dn_plan else null,
+            C.c_void_p(self.down_psi[buf] + dn_plan.recv_from_up()[0] * rb) if dn_plan else null,
+            C.c_size_t(p.halo * self.cols), C.c_void_p(self.state_ptr), C.c_void_p(self.flags_ptr),
+            C.c_void_p(self.up_flags) if up_plan else null, C.c_void_p(self.down_flags) if dn_plan else null,
+            float(timeout_seconds), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def status(self):
+        """(exchanges completed, waits that timed out) -- synchronises the device."""
+        epoch, timeouts = C.c_ulonglong(), C.c_ulonglong()
+        with torch.cuda.device(self.device):
+            self._lib.call("nlsb_dev_halo_status", C.c_void_p(self.state_ptr), C.byref(epoch), C.byref(timeouts))
+        return int(epoch.value), int(timeouts.value)
+
+    def close(self):
+        lib = self._lib.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for ptr in self._mapped:
+                lib.nlsb_peer_close(C.c_void_p(ptr))
+            self._mapped = []
+            self.psi = []
+            for ptr in self._own:
+                lib.nlsb_peer_free(C.c_void_p(ptr))
+            self._own = []
+
+
 class SlabGrid2D(object):
     """One n x n grid advanced by `world` ranks, each owning a slab of rows (BASELINE config 4).
 
@@ -174,7 +286,11 @@ class SlabGrid2D(object):
     """
 
     def __init__(self, n, dx, dt, order=5, pumping=None, coeffs=None, u0=0.1, group=None, device=None, stepper=None,
-                 rank=None, world=None, halo_steps=None):
+                 rank=None, world=None, halo_steps=None, exchange=None):
+        """exchange: "peer" (device-initiated exchange over peer-mapped memory, CUDA graphs; default for the CUDA
+        steppers on interleaved slabs), "nccl" (host-issued isend/irecv through torch.distributed), "local" (peer
+        kernels between slabs of ONE process, linked afterwards by ``link_local_peers`` -- tests) or "none"
+        (no exchange of its own: ``advance_emulated`` copies the halos)."""
         self.group = group
         if rank is not None or world is not None:
             # explicit placement: several slabs emulated inside one process (see advance_emulated)
@@ -220,6 +336,49 @@ class SlabGrid2D(object):
         self.cur = 0
         self.steps_done = 0
         self.side = torch.cuda.Stream(device=self.device) if self.on_gpu else None
+        # ---- how halos travel --------------------------------------------------------------------------
+        explicit = rank is not None or world is not None
+        if exchange is None:
+            exchange = "none" if explicit else ("peer" if (self.on_gpu and not self.planar and self.world > 1) else "nccl")
+        if exchange in ("peer", "local") and (self.planar or not self.on_gpu):
+            raise ValueError("exchange=%r needs the interleaved CUDA stepper" % exchange)
+        self.exchange, self.peer, self.graphs, self.exchange_note = exchange, None, {}, ""
+        self.use_graphs = True
+        if exchange in ("peer", "local") and self.world > 1:
+            try:
+                self._setup_peer(psi0, local=(exchange == "local"))
+            except Exception as exc:            # peer mapping refused (no NVLink / IPC disabled): host-issued exchange
+                if exchange == "local":
+                    raise
+                self.exchange, self.peer = "nccl", None
+                self.exchange_note = "peer mapping failed (%s); using NCCL isend/irecv" % (str(exc)[:160],)
+            if not explicit and dist.is_initialized():
+                # every rank must have taken the same decision
+                ok = torch.tensor([1 if self.exchange == "peer" else 0], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok.item()) == 0 and self.exchange == "peer":
+                    self.peer.close()
+                    self.peer, self.exchange = None, "nccl"
+                    self.psi = [psi0, torch.zeros_like(psi0)]
+                    self.exchange_note = "a neighbour could not map peer memory; using NCCL isend/irecv"
+
+    def _setup_peer(self, psi0, local):
+        """Move the psi buffers into exportable allocations, exchange IPC handles with the neighbours and map
+        theirs; warm the step kernel up (function attributes, tensor maps) so that the cycle can be captured."""
+        p = self.plan
+        peer = _PeerSlab(p, self.n, self.device)
+        peer.psi[0].copy_(psi0)
+        self.psi = peer.psi
+        self.peer = peer
+        if not local:
+            mine = peer.handles()
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=self.group)
+            peer.connect(everyone[p.up] if p.up is not None else None, everyone[p.down] if p.down is not None else None)
+            dist.barrier(group=self.group)
+        # one throw-away step 0 -> 1 over the rows the first real step also writes (same values)
+        self.stepper(self.psi[0], self.psi[1], self.pumping, *p.step_rows(0))
+        torch.cuda.synchronize(self.device)
 
     def _load(self, buf, value, with_halo):
         """Fill a local buffer (owned rows and, from a full array, the halo rows inside the domain)."""
@@ -256,7 +415,71 @@ class SlabGrid2D(object):
                 work.wait()
 
     # ---- time stepping -----------------------------------------------------------------------------
+    # ---- device-initiated exchange (peer-mapped memory): m steps + one exchange kernel, replayed from a graph --------
+    def _peer_step(self):
+        """One RK4 launch on the rows that are still valid, then -- after the m-th step -- the exchange kernel."""
+        p = self.plan
+        src, dst = self.psi[self.cur], self.psi[1 - self.cur]
+        self.stepper(src, dst, self.pumping, *p.step_rows(self.since_exchange))
+        self.cur = 1 - self.cur
+        self.since_exchange += 1
+        if self.since_exchange == p.halo_steps:
+            self.peer.exchange(self.cur)
+            self.since_exchange = 0
+        self.steps_done += 1
+
+    def _cycle_steps(self):
+        m = self.plan.halo_steps
+        return m if m % 2 == 0 else 2 * m        # a replayed cycle must start and end in the same psi buffer
+
+    def _cycle_graph(self):
+        """The CUDA graph of one cycle starting from the current buffer (captured on first use)."""
+        from . import _lib
+        key = self.cur
+        if key not in self.graphs:
+            lib = _lib.load()
+            before = lib.nlsb_kernel_launches()
+            graph = torch.cuda.CUDAGraph()
+            state = (self.cur, self.since_exchange, self.steps_done)
+            with torch.cuda.graph(graph, capture_error_mode="relaxed"):
+                for _ in range(self._cycle_steps()):
+                    self._peer_step()
+            kernels = lib.nlsb_kernel_launches() - before      # recorded, not run
+            lib.nlsb_add_kernel_launches(C.c_ulonglong((1 << 64) - kernels))
+            self.cur, self.since_exchange, self.steps_done = state
+            self.graphs[key] = (graph, int(kernels))
+        return self.graphs[key]
+
+    def prepare(self, iters):
+        """Capture the graph(s) an ``advance(iters)`` from the current state would replay, without running anything
+        (graph capture synchronises the device: slabs emulated inside one process capture before any of them starts)."""
+        if self.peer is not None and self.use_graphs and self.since_exchange == 0 and int(iters) >= self._cycle_steps():
+            with torch.cuda.device(self.device):
+                self._cycle_graph()
+        return self
+
+    def _advance_peer(self, iters):
+        from . import _lib
+        iters = int(iters)
+        cycle = self._cycle_steps()
+        with torch.cuda.device(self.device):
+            while iters > 0:
+                if self.use_graphs and self.since_exchange == 0 and iters >= cycle:
+                    graph, kernels = self._cycle_graph()
+                    replays = iters // cycle
+                    for _ in range(replays):
+                        graph.replay()
+                    _lib.load().nlsb_add_kernel_launches(C.c_ulonglong(kernels * replays))
+                    self.steps_done += replays * cycle
+                    iters -= replays * cycle
+                else:
+                    self._peer_step()
+                    iters -= 1
+        return self
+
     def advance(self, iters):
+        if self.peer is not None:
+            return self._advance_peer(iters)
         p = self.plan
         top, bottom, interior = p.strips()
         for _ in range(int(iters)):
@@ -325,9 +548,19 @@ class SlabGrid2D(object):
         return buf[lo:hi]
 
     def set_local_state(self, other_buffer):
-        """Overwrite the current state buffer (same layout) -- used by bench.py to reset between runs."""
+        """Overwrite the current state buffer (same layout, halo rows included) -- used by bench.py to reset between
+        runs.  Only valid right after an exchange (or at the start)."""
+        if self.since_exchange != 0:
+            raise RuntimeError("set_local_state between two halo exchanges")
         self.psi[self.cur].copy_(other_buffer)
-        self.since_exchange = 0
+
+    def close(self):
+        """Release peer mappings and graphs (call on every rank before the process group is destroyed)."""
+        self.graphs = {}
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+            self.psi = []
 
     def state_buffer(self):
         return self.psi[self.cur]
@@ -374,4 +607,33 @@ def advance_emulated(slabs, iters):
         for g in slabs:
             g.cur = 1 - g.cur
             g.steps_done += 1
+    return slabs
+
+
+def link_local_peers(slabs):
+    """Connect slabs built with ``exchange="local"`` inside ONE process (plain pointers instead of IPC mappings)."""
+    slabs = sorted(slabs, key=lambda g: g.rank)
+    for g in slabs:
+        g.peer.connect_local(slabs[g.rank - 1].peer if g.plan.up is not None else None,
+                             slabs[g.rank + 1].peer if g.plan.down is not None else None)
+    return slabs
+
+
+def advance_emulated_peer(slabs, iters, streams=None):
+    """Advance slabs linked by ``link_local_peers`` with the PRODUCT exchange kernel: every slab runs its own
+    ``advance`` on its own stream (the exchange kernels of neighbouring slabs wait for each other on the device, so
+    they must be able to run concurrently).  One GPU stands in for several."""
+    slabs = sorted(slabs, key=lambda g: g.rank)
+    dev = slabs[0].device
+    if streams is None:
+        streams = [torch.cuda.Stream(device=dev) for _ in slabs]
+    main = torch.cuda.current_stream(dev)
+    for g in slabs:
+        g.prepare(iters)
+    for g, st in zip(slabs, streams):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            g.advance(iters)
+    for st in streams:
+        main.wait_stream(st)
     return slabs

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Distributed check of the slab path over NCCL; run on a multi-GPU box:
+"""Distributed check of the slab path (peer-mapped exchange kernel and NCCL isend/irecv); run on a multi-GPU box:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/run_slab_nccl.py
@@ -30,19 +30,27 @@ def main():
 
     ok = True
     # 512: planar slabs + TMA tile kernel; 2048: interleaved slabs + strip-marching kernel (>= 2^20 owned nodes)
-    for n, iters in ((512, 40), (2048, 6)):
+    # 2048 twice: device-initiated exchange over peer-mapped memory (default), then host-issued NCCL
+    for n, iters, exchange in ((512, 40, None), (2048, 22, None), (2048, 6, "nccl")):
         m = model_2d(n, iters, radius=min(10.0, n * 0.1 / 4))
         u0 = 0.1 + 0.05 * rough_field((n, n), 5)
-        slab = SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0)
+        slab = SlabGrid2D(n, m.dx, m.dt, 5, m.getPumping(), m.getCoefficients(), u0, exchange=exchange)
         full = slab.advance(iters).gather()
+        how = "exchange %s%s" % (slab.exchange, (" [" + slab.exchange_note + "]") if slab.exchange_note else "")
+        if slab.peer is not None:
+            epoch, timeouts = slab.peer.status()
+            how += ", %d exchanges, %d time-outs, halo steps %d" % (epoch, timeouts, slab.plan.halo_steps)
+            if timeouts:
+                ok = False
+        slab.close()
         if rank == 0:
             from oracle import oracle as O
             single = Grid2D(n, m.dx, m.dt, order=5, pumping=m.getPumping(), coeffs=m.getCoefficients(), u0=u0)
             single = single.advance(iters).solution()[0]
             bitwise = bool(np.array_equal(full, single))
             err = rel_l2(full, O.dp.solve_nls_2d(m.dt, m.dx, 5, iters, m.getPumping(), m.getCoefficients(), u0))
-            print("slabs %d^2 over %d ranks (%s layout): bitwise equal to 1 GPU: %s, rel-L2 vs oracle %.2e"
-                  % (n, world, "planar" if slab.planar else "interleaved", bitwise, err))
+            print("slabs %d^2 over %d ranks (%s layout, %s): bitwise equal to 1 GPU: %s, rel-L2 vs oracle %.2e"
+                  % (n, world, "planar" if slab.planar else "interleaved", how, bitwise, err))
             ok = ok and bitwise and err <= 1e-10
 
     # ensemble sharding: each rank advances its members; results gathered and compared with one launch

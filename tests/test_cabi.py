@@ -129,5 +129,11 @@ def test_kernel_choice_and_stream_geometry_for_the_baseline_configs():
         assert (chunk + 6 * k) % (2 * (2 * k + 1)) == 0 and chunk >= 1
         ctas = strips * -(-n // chunk) * batch
         assert ctas >= 140                          # at least ~one CTA per SM
-    assert plan(256, 1024)[1] == 128                # C5 members: the two-CTAs-per-SM shape costs no extra columns
-    assert plan(1, 8192)[1:3] == [256, 35]
+    # order 5: two 128-thread CTAs per SM are faster per swept column than one 256-thread CTA (measured), which
+    # outweighs their wider relative halo; order 3 keeps 256, order 7 has a single shape
+    assert plan(256, 1024)[1] == 128 and plan(1, 8192)[1:3] == [128, 74]
+    assert plan(1, 4096, 3)[1] == 256 and plan(1, 4096, 7)[1] == 192
+    # a 1024-row slab of the 8192-column grid with its deep halo (multi-GPU): exactly one wave of 2 x 148 CTAs
+    out = [C.c_int() for _ in range(4)]
+    assert lib.nlsb_dev_rk4_2d_plan(1, 1072, 8192, 5, *[C.byref(v) for v in out]) == 0
+    assert out[2].value * -(-1072 // out[3].value) == 296
