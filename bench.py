@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- grid-point RK-steps per second of the daskol/nls hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload c4] [--also c2,c3,c5]
 
-A bench "step" is one pass of the hot path over the workload: one ``solve`` of `iters` RK4 steps.
-Default workload at every N is BASELINE.json configs[1] (C2: 2D 512 x 512 ring pumping, 5000 RK
-steps, order 5).  C2 does not shard ("replicas only"), so with --gpus N every rank
-advances its own replica (weak scaling, no data-path collective).  Other workloads (--workload c1,
-c3, c4, c5) are for DESIGN.md / profiles, not the driver's bench line.
+Headline workload (default, every N): BASELINE.json config 4 (C4) -- ONE 8192 x 8192 complex128 grid, ring pump,
+order 5.  A bench "step" is one pass of the hot path over that grid: `rk_steps_per_bench_step` (200)
+RK4 steps.  With --gpus 1 the grid lives on one GPU (strip-marching kernel, one launch per RK step); with --gpus N > 1
+the SAME grid is cut into N row slabs (strong scaling) and the halos travel over NVLink on the data path: a
+device-initiated exchange kernel over peer-mapped memory inside a CUDA graph (nls_b200/multigpu.py, csrc/peer.cu),
+or NCCL isend/irecv when peer mapping is refused -- `config.partition` says which.
 
-Output: ONE JSON line on rank 0 (see the keys in `main`).  `value` is device-timed with inputs resident
-in HBM; `e2e` goes through the f2py-signature entry point ``nls_b200.native.nls.solve_nls_2d`` with
-pinned HOST buffers (H2D + D2H inside the timed region).  `--impl reference` times the CPU oracle
-(``oracle/``: the C restatement of nls.f90 in the reference's own single precision -- the reference's
-Fortran cannot be compiled in this image) on a bounded sample of the same workload.
+The other BASELINE configs ride in the same JSON line as sub-records under "also" (each with value, roofline
+fraction, clocks): C2 (512^2, 5000 steps, replicas), C3 (65 536 x 1D n=1000, full 10 000-step horizon, members
+sharded over the ranks), C5 (256 x 1024^2, members sharded).  `--workload cN` makes any of them the headline
+instead (profiling / DESIGN.md tables).
+
+Output: ONE JSON line on rank 0.  `value` is device-timed (CUDA events on the launching stream, max over ranks) with
+inputs resident in HBM; `e2e` goes through the reference-facing entry point ``nls_b200.native.nls.solve_nls_2d``
+(C ABI nlsb_solve_nls_2d) with pinned HOST buffers, H2D + D2H inside the timed region (slabs: every rank uploads and
+downloads its rows through ``SlabGrid2D.upload / download``).  `--impl reference` times the CPU oracle (``oracle/``:
+the C restatement of nls.f90 in the reference's own single precision -- the reference's Fortran cannot be compiled
+in this image) on a bounded sample of the same workload.
 """
 
 import argparse
@@ -34,31 +41,22 @@ METRIC = "grid-point RK-steps/sec"
 UNIT = "point-steps/s"
 BYTES_PER_POINT_STEP = 40.0      # read psi 16 + read P 8 + write psi 16
 
-# DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the
-# `ncu --set full` captures summarised under profiles/ (round 1, default kernels).  C2's working set is
-# L2-resident: the figure is the cold-cache replay ncu measures, in steady state it is ~0.
-NCU_TRAFFIC = {
-    "c2": (6.32e6, "profiles/r1_ncu_tma64_pdl_c2_512_default.txt (cold L2 under ncu; L2-resident in steady state)"),
-    "c4": (2.716e9, "profiles/r1_ncu_stream_c4_8192.txt"),
-}
-# FP64-pipe utilisation of the dominant kernel (sm__pipe_fp64_cycles_active, same ncu captures): the path is bound
-# by FP64 issue + shared-memory traffic, not by HBM -- reported beside the HBM roofline fraction.
-NCU_FP64_PIPE_PCT = {"c2": 39.6, "c3": 67.4, "c4": 66.1}
-DOMINANT_KERNEL = {"c1": "rk4_1d_resident (whole time loop, one launch)", "c3": "rk4_1d_resident (whole time loop, one launch)",
-                   "c2": "rk4_step_fused_kernel (TMA tile kernel, 32x64 tiles, one RK4 step per launch)",
-                   "c4": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)",
-                   "c5": "rk4_stream_kernel (strip-marching kernel, one RK4 step per launch)"}
+DOMINANT_KERNEL = {"c1": "rk4_1d_resident", "c3": "rk4_1d_resident", "c2": "rk4_step_fused_kernel",
+                   "c4": "rk4_stream_kernel", "c5": "rk4_stream_kernel"}
+KERNEL_NOTE = {"c1": "whole time loop in one launch", "c3": "whole time loop in one launch",
+               "c2": "TMA tile kernel, 32x64 tiles, one RK4 step per launch",
+               "c4": "strip-marching kernel, one RK4 step per launch", "c5": "strip-marching kernel, one RK4 step per launch"}
 
 ORIG = dict(R=0.0242057488654, gamma=0.0242057488654, g=0.00162178517398, tilde_g=0.0169440242057,
             gamma_R=0.242057488654)
 
 WORKLOADS = {
-    # name: dim, n, batch, iters (per bench step), description
+    # name: dim, n, batch, iters = RK steps per bench step, description
     "c1": dict(dim=1, n=400, batch=1, iters=10000, desc="examples/solve1d.py: 1D radial n=400, ring pump, 10000 RK steps, order 5"),
     "c2": dict(dim=2, n=512, batch=1, iters=5000, desc="examples/solve2d.py at 512x512: 2D ring pump, 5000 RK steps, order 5"),
-    "c3": dict(dim=1, n=1000, batch=65536, iters=1000, desc="1D ensemble 65536 members (256 powers x 256 reservoir rates), n=1000, order 5"),
-    "c4": dict(dim=2, n=8192, batch=1, iters=20, desc="2D 8192x8192 ring pump radius 200 var 50, order 5"),
-    "c5": dict(dim=2, n=1024, batch=256, iters=20, desc="2D ensemble 256 x 1024x1024, pump radius 2..40, order 5"),
+    "c3": dict(dim=1, n=1000, batch=65536, iters=10000, desc="1D ensemble 65536 members (256 powers x 256 reservoir rates), n=1000, 10000 RK steps, order 5"),
+    "c4": dict(dim=2, n=8192, batch=1, iters=200, desc="2D 8192x8192 complex128 grid, ring pump radius 200 var 50, order 5, 200 RK steps per pass"),
+    "c5": dict(dim=2, n=1024, batch=256, iters=100, desc="2D ensemble 256 x 1024x1024, pump radius 2..40, order 5, 100-step window of the 1e5-step horizon"),
 }
 
 
@@ -153,11 +151,12 @@ class ClockSampler(object):
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, smax, reasons = [], [], set()
+        sm, smax, watts, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
+                watts.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, val in zip(self.NAMES, r[3:7]):
@@ -166,7 +165,7 @@ class ClockSampler(object):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_mhz_min": float(min(sm)), "power_w_max": float(max(watts))}
 
 
 def measured_hbm_peak():
@@ -178,20 +177,41 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_record(name):
+    """What the committed ncu capture of this workload's dominant kernel says (profiles/ncu_index.json, written by
+    tools/ncu_index.py from the .ncu-rep files; every entry names its capture file and the commit it was taken at).
+    Archived evidence, not something this run measured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_index.json")) as fh:
+            return json.load(fh).get(name)
+    except Exception:
+        return None
+
+
 # ---- reference arm: the CPU oracle ------------------------------------------------------------------
-def cpu_sample(w, kind="sp", budget_points=1.0e8):
-    """Times the oracle on a bounded sample of workload `w`: one member, `s` RK steps (about 10-25 s of CPU work
-    for the 2D workloads at the oracle's ~5-9e6 point-steps/s; a 1D member's whole horizon is shorter than that)."""
+CPU_RATE_GUESS = 5.5e6      # sp oracle, point-steps/s on one core, out-of-cache 2D grids (sizes the samples only)
+
+
+def cpu_sample(w, kind="sp", budget_s=15.0):
+    """Times the oracle on a bounded sample of workload `w`: ONE member; 2D grids larger than 4096^2 are sampled on
+    their central 4096 x 4096 crop (same pumping values, far out of cache like the full grid); as many RK steps as
+    fit `budget_s` seconds at the oracle's ~5e6 point-steps/s (at least 1, at most the workload's own horizon)."""
     from oracle import oracle as O
     k = O.sp if kind == "sp" else O.dp
-    per_step = w["n"] if w["dim"] == 1 else w["n"] ** 2
-    s = int(max(2, min(w["iters"], budget_points // per_step)))
     P, c, u0 = w["pumping"][0], w["coeffs"][0], w["u0"][0]
+    n = w["n"]
+    crop = ""
+    if w["dim"] == 2 and n > 4096:
+        lo = (n - 4096) // 2
+        P, u0, n = np.ascontiguousarray(P[lo:lo + 4096, lo:lo + 4096]), np.ascontiguousarray(u0[lo:lo + 4096, lo:lo + 4096]), 4096
+        crop = "central 4096x4096 crop of "
+    per_step = n if w["dim"] == 1 else n * n
+    s = int(max(1, min(w["iters"], budget_s * CPU_RATE_GUESS // per_step)))
     fn = k.solve_nls if w["dim"] == 1 else k.solve_nls_2d
     t0 = time.perf_counter()
     fn(w["dt"], w["dx"], w["order"], s, P, c, u0)
     dt = time.perf_counter() - t0
-    sample = "1 member of %s, %d RK steps (%d point-steps), %s oracle, 1 thread" % (w["name"], s, per_step * s, kind)
+    sample = "%s1 member of %s, %d RK steps (%d point-steps), %s oracle, 1 thread" % (crop, w["name"], s, per_step * s, kind)
     return per_step * s / dt, dt, sample
 
 
@@ -200,20 +220,24 @@ def run_reference(args):
     if rank != 0:
         return
     w = build_inputs(args.workload, args.iters, 1 if WORKLOADS[args.workload]["batch"] > 1 else None)
+    # the whole run (K timed + W warm-up samples) stays within a few minutes: at most ~150 s of timed samples
+    budget = max(2.0, min(20.0, 150.0 / max(args.steps, 1)))
     for _ in range(args.warmup):
-        cpu_sample(w, "sp", budget_points=2.0e6)
+        cpu_sample(w, "sp", budget_s=0.3)
     total_pts, total_t, sample = 0.0, 0.0, ""
     for _ in range(args.steps):
-        rate, dt, sample = cpu_sample(w, "sp")
+        rate, dt, sample = cpu_sample(w, "sp", budget_s=budget)
         total_pts += rate * dt
         total_t += dt
     value = total_pts / total_t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if args.gpus > 1 and args.workload in ("c3", "c4", "c5") else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "name": w["name"],
-                   "note": "reference algorithm is serial; one bounded sample per step"},
+                   "note": "the reference algorithm is serial (no threads in nls.f90): one bounded sample per step, "
+                           "normalised per point-step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,171 +246,277 @@ def run_reference(args):
 
 
 # ---- engine arm -------------------------------------------------------------------------------------
-def run_engine(args):
+class Env(object):
+    """Process placement and the torch.distributed plumbing of one bench run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl engine needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        assert self.world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+        self.flush = None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_l2(self):
+        if self.flush is None:
+            self.flush = self.torch.empty(256 * 1024 * 1024, dtype=self.torch.uint8, device=self.dev)   # > 126 MB L2
+        self.flush.zero_()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+def merge_clocks(env, mine):
+    """Rank 0's record plus the worst case over the ranks (lowest median clock, union of the reasons)."""
+    everyone = env.gather_objects(mine)
+    out = dict(mine)
+    if len(everyone) > 1:
+        meds = [c["sm_mhz"] for c in everyone if c.get("sm_mhz")]
+        out["sm_mhz_min_over_ranks"] = min(meds) if meds else None
+        out["reasons"] = sorted(set(r for c in everyone for r in c.get("reasons", [])))
+        out["samples_per_rank"] = [c.get("samples", 0) for c in everyone]
+    return out
+
+
+def measure(env, args, name, steps, warmup, iters=None, warmup_iters=None, with_e2e=False):
+    """Device-timed throughput of workload `name` on env.world GPUs; returns the record (dict) on every rank."""
     import torch
-    import torch.distributed as dist
     from nls_b200 import _lib
     from nls_b200.engine import Ensemble1D, Grid2D
-    from nls_b200.native import nls
-    from nls_b200.engine import set_2d_path
-    set_2d_path(args.path)
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl engine needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
-
-    name = args.workload
     spec = WORKLOADS[name]
-    # ensembles shard their members across ranks (strong scaling); single systems run as replicas (weak)
-    shard = spec["batch"] > 1
-    batch = None
-    if args.batch:
-        batch = args.batch
-    total_batch = batch if batch else spec["batch"]
+    world, rank, dev = env.world, env.rank, env.dev
+    shard = spec["batch"] > 1                               # ensembles: members sharded over the ranks
+    total_batch = args.batch if (args.batch and name == args.workload) else spec["batch"]
     members = (rank * total_batch // world, (rank + 1) * total_batch // world) if shard else None
-    w = build_inputs(name, args.iters, batch, args.n, members)      # a rank builds only the members it owns
-    if args.order:
+    w = build_inputs(name, iters, total_batch if shard else None, args.n if name == args.workload else None, members)
+    if args.order and name == args.workload:
         w["order"] = args.order
         w["desc"] += " [order overridden: %d]" % args.order
     if shard:
         w["batch"] = members[1] - members[0]
     iters = w["iters"]
-    dev = torch.device("cuda", local)
-
     slabs = name == "c4" and world > 1     # one big grid: slab decomposition with halo exchange (strong scaling)
     if slabs:
         from nls_b200.multigpu import SlabGrid2D
-        eng = SlabGrid2D(w["n"], w["dx"], w["dt"], w["order"], w["pumping"][0], w["coeffs"][0], w["u0"][0], device=dev)
-        psi0 = eng.state_buffer().clone()
+        eng = SlabGrid2D(w["n"], w["dx"], w["dt"], w["order"], w["pumping"][0], w["coeffs"][0], w["u0"][0], device=dev,
+                         exchange=args.exchange)
+        state = lambda: eng.state_buffer()
     elif w["dim"] == 1:
         eng = Ensemble1D(w["n"], w["dx"], w["dt"], order=w["order"], batch=w["batch"], pumping=w["pumping"],
                          coeffs=w["coeffs"], u0=w["u0"], device=dev)
-        psi0 = eng.psi.clone()
+        state = lambda: eng.psi
     else:
         eng = Grid2D(w["n"], w["dx"], w["dt"], order=w["order"], batch=w["batch"], pumping=w["pumping"],
                      coeffs=w["coeffs"], u0=w["u0"], device=dev)
-        psi0 = eng.psi.clone()
+        state = lambda: eng.psi
+    # Grids far larger than the 126 MB L2 stream from HBM whatever ran before: the time loop simply continues from
+    # step to step.  Small working sets are reset to the initial field and the L2 is flushed between timed steps.
+    local_bytes = BYTES_PER_POINT_STEP * (points(w) // world if slabs else points(w))   # psi in + psi out + P
+    resident = local_bytes > 2 * 126e6
+    psi0 = None if resident else state().clone()
 
-    def reset():
-        eng.set_local_state(psi0) if slabs else eng.psi.copy_(psi0)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def one_step(timed):
-        reset()
-        flush.zero_()
+    def one_step(n_iters, timed):
+        if not resident:
+            state().copy_(psi0)
+            env.flush_l2()
+        a = b = None
         if timed:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            eng.advance(iters)
+        eng.advance(n_iters)
+        if timed:
             b.record()
-            return a, b
-        eng.advance(iters)
-        return None
+        return a, b
 
-    for _ in range(args.warmup):
-        one_step(False)
-    barrier()
+    for _ in range(warmup):
+        one_step(warmup_iters or iters, False)
+    env.barrier()
     launches0 = _lib.kernel_launches()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(env.local) as clocks:
         t_wall0 = time.perf_counter()
-        events = [one_step(True) for _ in range(args.steps)]
-        barrier()
+        events = [one_step(iters, True) for _ in range(steps)]
+        env.barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = _lib.kernel_launches() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in events)
-    final = (eng.state_buffer() if slabs else eng.psi).clone()
+    dev_ms_max, launches_max = env.max_over_ranks([dev_ms, float(launches)])
 
-    # end to end: host buffers through the reference-facing entry point (H2D + solve + D2H per step)
-    e2e = None
-    if name in ("c1", "c2", "c4") and not slabs:
-        P_h = torch.from_numpy(np.ascontiguousarray(w["pumping"][0])).pin_memory().numpy()
-        u_h = torch.from_numpy(np.ascontiguousarray(w["u0"][0])).pin_memory().numpy()
-        c_h = w["coeffs"][0]
-        fn = nls.solve_nls if w["dim"] == 1 else nls.solve_nls_2d
-        for _ in range(max(1, min(args.warmup, 3))):
-            out = fn(w["dt"], w["dx"], w["order"], iters, P_h, c_h, u_h)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            flush.zero_()
-            out = fn(w["dt"], w["dx"], w["order"], iters, P_h, c_h, u_h)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        e2e_ok = bool(np.array_equal(out, final[0].cpu().numpy()))
-        e2e = (e2e_s, P_h.nbytes + u_h.nbytes + c_h.nbytes, out.nbytes, e2e_ok)
-
-    # max over ranks
-    t = torch.tensor([dev_ms, e2e[0] if e2e else 0.0, float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
-
-    n_side = args.n if args.n else spec["n"]
-    total_points = (total_batch * (n_side if spec["dim"] == 1 else n_side * n_side)) if shard else points(w) * (1 if slabs else world)
-    work = float(total_points) * iters * args.steps
-    value = work / (dev_ms_max * 1e-3)
+    n_side = w["n"]
+    per_member = n_side if spec["dim"] == 1 else n_side * n_side
+    total_points = total_batch * per_member if shard else per_member * (1 if slabs else world)
+    points_per_gpu = per_member // world if slabs else points(w)
+    value = float(total_points) * iters * steps / (dev_ms_max * 1e-3)
     peak, peak_src = measured_hbm_peak()
-    per_gpu_rate = value / world
-    achieved = BYTES_PER_POINT_STEP * per_gpu_rate / 1e9
-    launches_per_gpu = max(int(t[2]), 1)
-    # algorithmic bytes of one launch of the dominant kernel and its average duration over the timed region
+    achieved = BYTES_PER_POINT_STEP * (value / world) / 1e9
     rk_per_launch = iters if w["dim"] == 1 else 1
-    bytes_per_launch = BYTES_PER_POINT_STEP * (points(w) // world if slabs else points(w)) * rk_per_launch
-    dominant_launches = args.steps * (1 if w["dim"] == 1 else iters)
-    traffic = NCU_TRAFFIC.get(name, (None, None)) if args.path == "auto" and not slabs else (None, None)
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "strong" if (shard or slabs) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "name": name, "rk_steps_per_bench_step": iters,
-                   "points_per_gpu": (points(w) // world if slabs else points(w)), "partition": ("members sharded across ranks" if shard else
-                                 "row slabs, 4k-row halo exchange per RK step over NCCL" if slabs else "replicas only"),
-                   "kernels_2d": args.path,
-                   "l2": "256 MiB flush buffer written between timed steps; 512^2 working set is L2-resident by nature",
+    dominant_launches = steps * (1 if w["dim"] == 1 else iters)
+    if slabs:
+        partition = ("row slabs (strong scaling), %d-row halos, one exchange per %d RK steps, %s; %.1f %% of a rank's rows "
+                     "recomputed redundantly between exchanges"
+                     % (eng.plan.halo, eng.plan.halo_steps,
+                        {"peer": "device-initiated exchange kernel over peer-mapped memory (NVLink), m-step cycle in a CUDA graph",
+                         "nccl": "host-issued NCCL isend/irecv"}[eng.exchange] + ((" [" + eng.exchange_note + "]") if eng.exchange_note else ""),
+                        100.0 * eng.plan.step_halo * (eng.plan.halo_steps - 1) / max(eng.plan.rows_local, 1)))
+    else:
+        partition = "members sharded across ranks, no data-path collective" if shard else "replicas only"
+    rec = {
+        "value": value, "unit": UNIT, "ms_per_step": dev_ms_max / steps, "steps": steps, "warmup": warmup,
+        "scaling": "strong" if (shard or slabs) else "weak",
+        "config": {"workload": w["desc"], "name": name, "rk_steps_per_bench_step": iters, "points_per_gpu": points_per_gpu,
+                   "partition": partition, "kernels_2d": args.path,
+                   "l2": ("per-GPU working set of %.0f MB (psi in, psi out, pumping) > 2 x the 126 MB L2: every step streams "
+                          "from HBM, the time loop continues from step to step" % (local_bytes / 1e6)) if resident else
+                         "field reset and a 256 MiB buffer written (L2 flush) between timed steps; the working set is L2 / "
+                         "SM-resident by nature",
                    "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
-        "gpu_launches": int(t[2]),
+        "gpu_launches": int(launches_max),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic[0], "traffic_source": traffic[1], "peak_source": peak_src,
-                     "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(name) if args.path == "auto" else None,
-                     "kernel": DOMINANT_KERNEL[name],
-                     "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "peak_source": peak_src, "kernel": DOMINANT_KERNEL[name], "kernel_note": KERNEL_NOTE[name],
+                     "algorithmic_bytes_per_launch": BYTES_PER_POINT_STEP * points_per_gpu * rk_per_launch,
                      "avg_launch_us": 1e3 * dev_ms_max / dominant_launches,
                      "algorithmic_bytes": "40 B per point-step x point-steps per launch (DESIGN.md 3)",
-                     "per": "GPU", "launches_in_timed_region": launches_per_gpu},
+                     "per": "GPU", "launches_in_timed_region": int(launches_max)},
         "wall_s": t_wall,
     }
-    if e2e:
-        line["e2e"] = {"value": float(points(w)) * world * iters * args.steps / e2e_s_max, "unit": UNIT,
-                       "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]),
-                       "api": "nls_b200.native.nls.solve_nls%s (C ABI nlsb_solve_nls%s, pinned host buffers)"
-                              % (("", "") if w["dim"] == 1 else ("_2d", "_2d")),
-                       "matches_device_run": e2e[3]}
-    line["clocks"] = clocks.summary()
+    if slabs:
+        rec["roofline"]["avg_launch_us_note"] = "step time of the slowest rank / RK steps: includes its share of the exchange kernel"
+        epoch, timeouts = eng.peer.status() if eng.peer is not None else (None, 0)
+        rec["config"]["halo_exchanges_total"] = epoch
+        rec["config"]["halo_wait_timeouts"] = timeouts
+    archived = ncu_record(name) if (args.path == "auto" and not slabs) else None
+    rec["roofline"]["traffic"] = archived.get("dram_bytes_per_launch") if archived else None
+    if archived:
+        rec["roofline"]["ncu_archived"] = archived
+    rec["clocks"] = merge_clocks(env, clocks.summary())
 
-    if rank == 0:
-        if world == 1 and not args.no_cpu:
-            wc = build_inputs(name, args.iters, 1 if spec["batch"] > 1 else None)
-            rate, dt_cpu, sample = cpu_sample(wc, "sp")
-            rate_dp, _, sample_dp = cpu_sample(wc, "dp", budget_points=2.0e7)
+    # ---- end to end: host buffers through the reference-facing entry point (H2D + solve + D2H per step) ----
+    if with_e2e:
+        e2e = None
+        if slabs:
+            p = eng.plan
+            lo, hi = max(p.global_row0, 0), min(p.global_row0 + p.rows_alloc, p.n)
+            P_h = torch.zeros((p.rows_alloc, p.n), dtype=torch.float64).pin_memory()
+            u_h = torch.zeros((p.rows_alloc, p.n), dtype=torch.complex128).pin_memory()
+            P_h[lo - p.global_row0:hi - p.global_row0] = torch.from_numpy(w["pumping"][0][lo:hi])
+            u_h[lo - p.global_row0:hi - p.global_row0] = torch.from_numpy(w["u0"][0][lo:hi])
+            out_h = torch.empty((p.rows_local, p.n), dtype=torch.complex128).pin_memory()
+            for _ in range(2):
+                eng.upload(P_h, u_h).advance(iters).download(out_h)
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                eng.upload(P_h, u_h).advance(iters).download(out_h)
+            env.barrier()
+            e2e_s = time.perf_counter() - t0
+            e2e = (e2e_s, P_h.nbytes + u_h.nbytes, out_h.nbytes, None,
+                   "nls_b200.multigpu.SlabGrid2D.upload / advance / download (pinned host slabs per rank)")
+        elif name in ("c1", "c2", "c4"):
+            from nls_b200.native import nls
+            P_h = torch.from_numpy(np.ascontiguousarray(w["pumping"][0])).pin_memory().numpy()
+            u_h = torch.from_numpy(np.ascontiguousarray(w["u0"][0])).pin_memory().numpy()
+            c_h = w["coeffs"][0]
+            fn = nls.solve_nls if w["dim"] == 1 else nls.solve_nls_2d
+            for _ in range(2):
+                out = fn(w["dt"], w["dx"], w["order"], iters, P_h, c_h, u_h)
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                if not resident:
+                    env.flush_l2()
+                out = fn(w["dt"], w["dx"], w["order"], iters, P_h, c_h, u_h)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            check = bool(np.array_equal(out, state_after_one(env, args, w, iters)))
+            e2e = (e2e_s, P_h.nbytes + u_h.nbytes + c_h.nbytes, out.nbytes, check,
+                   "nls_b200.native.nls.solve_nls%s (C ABI nlsb_solve_nls%s, pinned host buffers)"
+                   % (("", "") if w["dim"] == 1 else ("_2d", "_2d")))
+        if e2e:
+            e2e_s_max = env.max_over_ranks([e2e[0]])[0]
+            rec["e2e"] = {"value": float(total_points) * iters * steps / e2e_s_max, "unit": UNIT,
+                          "h2d_bytes_per_step": int(e2e[1]), "d2h_bytes_per_step": int(e2e[2]), "api": e2e[4],
+                          "bytes_are": "per rank" if slabs else "per call", "ms_per_step": 1e3 * e2e_s_max / steps}
+            if e2e[3] is not None:
+                rec["e2e"]["matches_device_run"] = e2e[3]
+    if slabs:
+        eng.close()
+    return rec
+
+
+def state_after_one(env, args, w, iters):
+    """The device-resident engine's result for ONE pass from the initial field (what a host-buffer solve must equal)."""
+    from nls_b200.engine import Ensemble1D, Grid2D
+    if w["dim"] == 1:
+        eng = Ensemble1D(w["n"], w["dx"], w["dt"], order=w["order"], batch=1, pumping=w["pumping"], coeffs=w["coeffs"],
+                         u0=w["u0"], device=env.dev)
+    else:
+        eng = Grid2D(w["n"], w["dx"], w["dt"], order=w["order"], batch=1, pumping=w["pumping"], coeffs=w["coeffs"],
+                     u0=w["u0"], device=env.dev)
+    return eng.advance(iters).psi[0].cpu().numpy()
+
+
+def run_engine(args):
+    from nls_b200.engine import set_2d_path
+    set_2d_path(args.path)
+    env = Env(args)
+    name = args.workload
+    rec = measure(env, args, name, args.steps, args.warmup, iters=args.iters, with_e2e=True)
+    line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": rec["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": rec["config"],
+            "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"], "wall_s": rec["wall_s"]}
+    if "e2e" in rec:
+        line["e2e"] = rec["e2e"]
+    line["clocks"] = rec["clocks"]
+
+    also = [] if args.also == "none" else [a for a in args.also.split(",") if a and a != name]
+    if args.also == "default":
+        also = [a for a in (["c2", "c3", "c5"] if env.world == 1 else ["c3", "c5"]) if a != name]
+    line["also"] = {}
+    for other in also:
+        # shorter warm-up passes for the whole-horizon 1D launch; one timed pass of C3 is 6 s on one GPU
+        sub_steps = {"c2": 3, "c3": 1, "c5": 3, "c1": 3, "c4": 2}[other]
+        warm_iters = {"c3": 500}.get(other)
+        sub = measure(env, args, other, sub_steps, 3, warmup_iters=warm_iters)
+        line["also"][other] = {"value": sub["value"], "unit": UNIT, "frac": sub["roofline"]["frac"],
+                               "ms_per_step": sub["ms_per_step"], "steps": sub["steps"], "warmup": sub["warmup"],
+                               "scaling": sub["scaling"], "config": sub["config"], "roofline": sub["roofline"],
+                               "gpu_launches": sub["gpu_launches"], "clocks": sub["clocks"]}
+
+    if env.rank == 0:
+        if env.world == 1 and not args.no_cpu:
+            wc = build_inputs(name, args.iters, 1 if WORKLOADS[name]["batch"] > 1 else None)
+            rate, dt_cpu, sample = cpu_sample(wc, "sp", budget_s=15.0)
+            rate_dp, _, sample_dp = cpu_sample(wc, "dp", budget_s=4.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                     "host_cores": os.cpu_count(), "dp_value": rate_dp, "dp_sample": sample_dp}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -395,12 +525,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["engine", "reference"], default="engine")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c4")
+    ap.add_argument("--also", default="default", help="comma list of other workloads measured as sub-records, 'none', or "
+                    "'default' (c2,c3,c5 on one GPU; c3,c5 sharded on several)")
     ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
     ap.add_argument("--grid-n", dest="n", type=int, default=None, help="override the grid size (profiling only)")
     ap.add_argument("--order", type=int, default=None, help="override the stencil order (profiling only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default=None, help="halo transport of the slab run (default: peer)")
     ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "resident", "staged"], default="auto", help="2D kernel family")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":

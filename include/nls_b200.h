@@ -54,6 +54,10 @@ typedef void *nlsb_stream_t;   /* cudaStream_t */
 const char *nlsb_last_error(void);
 /* 1 if a CUDA device is usable by this process, else 0 (never raises). */
 int nlsb_device_available(void);
+/* Device scratch of the host-buffer entry points comes from a memory pool PRIVATE to this library and stays
+ * cached there between calls, as do the instantiated CUDA graphs of the 2D time loop; this returns both to
+ * the driver (call it when no nlsb_* work is in flight). */
+int nlsb_trim_memory(void);
 /* Number of CUDA kernels this library has launched since it was loaded (graph replays included). */
 unsigned long long nlsb_kernel_launches(void);
 
@@ -227,6 +231,24 @@ int nlsb_dev_diagnostics_1d(int batch, int n, int order, double dx, const double
 int nlsb_dev_diagnostics_2d(int batch, int rows, int cols, int order, double dx, const double *wx,
                             const double *wy, const double *pumping, const double *coeffs, const double *psi,
                             void *scratch, double *out8, nlsb_stream_t stream);
+/* Time loop with the diagnostics FUSED into it: as nlsb_dev_rk4_1d / nlsb_dev_rk4_2d, and
+ * out8[member][8] receives the diagnostics above of the state ENTERING the last of the `iters` (>= 1) steps -- that
+ * step's first stage holds H(psi) of that state, so the reduction rides in the same launch (1D: CTA-resident kernel;
+ * 2D: strip-marching kernel, per-CTA partial sums in diag_scratch + a fixed-order finishing launch).  The value is
+ * what nlsb_dev_diagnostics_* returns for the state after iters - 1 steps; the convergence loop of tools/check.py
+ * (solve a chunk, copy back, chemical potential) becomes one call per chunk with 8 doubles per member read back.
+ * Kernels without the fused reduction (tile kernel on small grids, per-stage paths, 1D n > 2048) run the stand-alone
+ * pass before their last step: same result.  diag_scratch: nlsb_dev_rk4_2d_diag_scratch() bytes (2D) or
+ * nlsb_dev_diagnostics_scratch() bytes (1D). */
+size_t nlsb_dev_rk4_2d_diag_scratch(int batch, int rows, int cols, int order);
+int nlsb_dev_rk4_2d_diag(int batch, int rows, int cols, int order, int iters, double dt, double dx, const double *wx,
+                         const double *wy, const double *pumping, const double *coeffs,
+                         const double *shared_coeffs_host, double *psi, void *workspace, size_t workspace_bytes,
+                         void *diag_scratch, double *out8, nlsb_stream_t stream);
+int nlsb_dev_rk4_1d_diag(int batch, int n, int order, int iters, double dt, double dx, const double *taps,
+                         const double *pumping, const double *coeffs, double *psi, void *diag_scratch, double *out8,
+                         nlsb_stream_t stream);
+
 
 /* Pumping profiles of an ensemble generated on the device, sampled on the reference's grid (nls/model.py:220-232:
  * dim 1: x = linspace(0, n dx, n); dim 2: x = y = linspace(-n dx/2, n dx/2, n), out[b][i][j] = P(x_j, y_i)).
@@ -235,6 +257,11 @@ int nlsb_dev_diagnostics_2d(int batch, int rows, int cols, int order, double dx,
  * Grid and arithmetic are bit-identical to numpy's, exp() may differ in the last place (<= 4 ulp in the result). */
 int nlsb_dev_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_host,
                               double *out, nlsb_stream_t stream);
+
+/* Self-test hook: fast[i] = a[i] / b[i] by the divide of the fused kernels (reciprocal seed + Newton step + residual
+ * correction, csrc/device_math.cuh), exact[i] = the correctly rounded IEEE quotient; device pointers.  The reservoir
+ * n = c12 P / (c13 + c14 |psi|^2) (nls.f90:580) is the only division on the path; its denominator is >= c13 > 0. */
+int nlsb_dev_divide_check(size_t n, const double *a, const double *b, double *fast, double *exact, nlsb_stream_t stream);
 
 /* ---- multi-GPU row slabs: peer-mapped buffers and the device-initiated halo exchange -----------------------
  * The reference has no parallelism; BASELINE.json config 4 asks for the 8192^2 grid cut into row

@@ -22,6 +22,7 @@ PROTOTYPES = {
     "nlsb_last_error": (C.c_char_p, []),
     "nlsb_device_available": (_I, []),
     "nlsb_kernel_launches": (C.c_ulonglong, []),
+    "nlsb_trim_memory": (_I, []),
     "nlsb_version": (None, [_P, _P, _P]),
     "nlsb_make_banded_matrix": (_I, [_I, _I, _P, _P]),
     "nlsb_clear_first_row_of_derivative": (_I, [_I, _I, _P]),
@@ -66,6 +67,7 @@ PROTOTYPES = {
     "nlsb_dev_rk4_step_2d_slab_planar": (_I, [_I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "nlsb_dev_hamiltonian_2d": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "nlsb_dev_cross_matvec_2d": (_I, [_I, _I, _I, _P, _P, _P, _P, _F, _P]),
+    "nlsb_dev_divide_check": (_I, [_Z, _P, _P, _P, _P, _P]),
     "nlsb_dev_reservoir": (_I, [_Z, _P, _P, _P, _P, _P]),
     "nlsb_dev_rk4_2d_plan": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "nlsb_dev_pumping_profiles": (_I, [_I, _I, _I, _I, _F, _P, _P, _P]),
@@ -79,6 +81,9 @@ PROTOTYPES = {
     "nlsb_dev_halo_status": (_I, [_P, _P, _P]),
     "nlsb_add_kernel_launches": (None, [C.c_ulonglong]),
     "nlsb_dev_diagnostics_scratch": (_Z, [_I]),
+    "nlsb_dev_rk4_2d_diag_scratch": (_Z, [_I, _I, _I, _I]),
+    "nlsb_dev_rk4_2d_diag": (_I, [_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P, _P, _P]),
+    "nlsb_dev_rk4_1d_diag": (_I, [_I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "nlsb_dev_diagnostics_1d": (_I, [_I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "nlsb_dev_diagnostics_2d": (_I, [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -56,6 +57,20 @@ namespace {
 
 bool valid_order(int m) { return m == 3 || m == 5 || m == 7; }
 
+// The fused kernels divide by c13 + c14 |psi|^2 with a reciprocal-seeded divide whose precondition is a finite,
+// normal, positive denominator (device_math.cuh): every model the reference's model.py builds has c13 = 1 and
+// c14 = R phi0^2 / gamma_R > 0 (model.py:157-159).  Coefficient sets outside that domain (where the reference's
+// own divide would produce +-inf / NaN fields anyway) are refused instead of being silently mis-divided.
+int check_coeffs(const double *c23)
+{
+    for (int i : {2, 3, 4, 5, 11, 12, 13})
+        if (!std::isfinite(c23[i])) return fail(NLSB_EINVAL, "coeffs[%d] is not finite", i);
+    if (!(c23[12] >= 1e-290) || !(c23[13] >= 0.0))
+        return fail(NLSB_EINVAL, "coeffs[12] (= %g) must be positive and coeffs[13] (= %g) non-negative: the reservoir "
+                                 "denominator c13 + c14 |psi|^2 must stay positive", c23[12], c23[13]);
+    return 0;
+}
+
 int check_order_size(int n, int order)
 {
     if (!valid_order(order)) return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
@@ -70,18 +85,34 @@ int internal_stream(cudaStream_t *out)
     int dev = 0;
     NLSB_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(NLSB_EINVAL, "device ordinal %d out of range", dev);
-    if (!streams[dev]) {
-        NLSB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
-        // keep the stream-ordered scratch allocations of the host entry points cached between calls:
-        // by default the pool hands memory back to the driver at every synchronisation
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
+    if (!streams[dev]) NLSB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
     *out = streams[dev];
+    return 0;
+}
+
+// The library's PRIVATE stream-ordered memory pool (one per device): scratch of the host-buffer entry points stays
+// cached here between calls (the default pool would hand it back to the driver at every synchronisation, and its
+// attributes belong to the embedding application).  nlsb_trim_memory() returns the cached memory to the driver.
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[64] = {};
+
+int private_pool(cudaMemPool_t *out)
+{
+    int dev = 0;
+    NLSB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(NLSB_EINVAL, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        NLSB_CUDA(cudaMemPoolCreate(&g_pools[dev], &props));
+        unsigned long long keep = ~0ull;      // keep freed blocks until nlsb_trim_memory
+        NLSB_CUDA(cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    *out = g_pools[dev];
     return 0;
 }
 
@@ -96,9 +127,11 @@ public:
     template <typename T>
     int alloc(T **out, size_t count)
     {
+        cudaMemPool_t pool;
+        NLSB_TRY(private_pool(&pool));
         void *p = nullptr;
-        cudaError_t e = cudaMallocAsync(&p, sizeof(T) * (count ? count : 1), stream_);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+        cudaError_t e = cudaMallocFromPoolAsync(&p, sizeof(T) * (count ? count : 1), pool, stream_);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync");
         ptrs_.push_back(p);
         *out = static_cast<T *>(p);
         return 0;
@@ -178,55 +211,108 @@ struct UniformCoeffsScope {
     ~UniformCoeffsScope() { g_uniform_coeffs = nullptr; }
 };
 
+// A request to reduce the scalar diagnostics of the state entering the LAST step of a time loop inside that step's
+// launch (strip-marching kernel): partial sums per CTA land in `partial`.
+struct DiagRequest {
+    void *partial;
+    double area;
+};
+
 // Fused path: one launch per RK step, psi ping-pongs between `psi` and the first plane of `work`.
 void enqueue_fused_steps_2d(int batch, int rows, int cols, int order, double dt, const CrossWeights &w,
                             const double *pumping, const double *coeffs, double2 *psi, double2 *work, int first_step,
-                            int nsteps, cudaStream_t stream, int *rc)
+                            int nsteps, cudaStream_t stream, int *rc, const DiagRequest *diag_on_last = nullptr)
 {
     Fused2DStep s{batch, rows, cols, 0, rows, 0, rows, nullptr, nullptr, pumping, coeffs, dt, g_uniform_coeffs};
     for (int i = 0; i < nsteps; ++i) {
         const bool even = ((first_step + i) & 1) == 0;
         s.in = even ? psi : work;
         s.out = even ? work : psi;
+        if (diag_on_last && i == nsteps - 1) {
+            s.diag_partial = diag_on_last->partial;
+            s.diag_area = diag_on_last->area;
+        }
         int r = launch_interleaved_step(order, s, w, stream);
         if (r && !*rc) *rc = r;
     }
 }
 
+// Instantiated graphs of 32-step chunks of the fused time loop, keyed by everything the captured launches depend
+// on (buffers, geometry, coefficients passed by value, kernel choice): repeated advance() / solve calls on the same
+// buffers replay the cached executable instead of capturing and instantiating again (milliseconds per call).
+struct LoopKey {
+    const void *psi, *work, *pumping, *coeffs;
+    int batch, rows, cols, order, path, device, has_uniform, tune[3];
+    double dt;
+    RhsCoeffs uniform;
+    CrossWeights w;
+};
+struct LoopGraph {
+    LoopKey key;
+    cudaGraphExec_t exec;
+    unsigned long long stamp;
+};
+std::mutex g_graph_mutex;
+LoopGraph g_graphs[8] = {};
+unsigned long long g_graph_stamp = 0;
+
 int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
-                         const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream)
+                         const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream,
+                         const DiagRequest *diag = nullptr)
 {
     int rc = 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     NLSB_CUDA(cudaStreamIsCapturing(stream, &cap));
     const int chunk = 32;   // even: a replayed chunk starts and ends in `psi`
     int done = 0;
-    if (cap == cudaStreamCaptureStatusNone && iters >= 2 * chunk) {
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        cudaStream_t rec;
-        NLSB_TRY(internal_stream(&rec));
-        NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
-        enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, &rc);
-        cudaError_t e = cudaStreamEndCapture(rec, &graph);
-        count_launches(0ull - (unsigned long long)chunk);
-        if (rc) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
+    const int replayable = diag ? iters - 1 : iters;      // the diagnostics-carrying last step is launched directly
+    if (cap == cudaStreamCaptureStatusNone && replayable >= 2 * chunk) {
+        LoopKey key;
+        std::memset(&key, 0, sizeof(key));
+        key.psi = psi; key.work = work; key.pumping = pumping; key.coeffs = coeffs;
+        key.batch = batch; key.rows = rows; key.cols = cols; key.order = order; key.path = g_path_2d.load();
+        NLSB_CUDA(cudaGetDevice(&key.device));
+        key.has_uniform = g_uniform_coeffs ? 1 : 0;
+        if (g_uniform_coeffs) key.uniform = *g_uniform_coeffs;
+        stream_2d_get_tuning(key.tune);
+        key.dt = dt;
+        key.w = w;
+        std::lock_guard<std::mutex> lock(g_graph_mutex);
+        LoopGraph *slot = nullptr, *victim = &g_graphs[0];
+        for (LoopGraph &g : g_graphs) {
+            if (g.exec && std::memcmp(&g.key, &key, sizeof(key)) == 0) slot = &g;
+            if (!g.exec || (victim->exec && g.stamp < victim->stamp)) victim = &g;
         }
-        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
-        e = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
-        for (; done + chunk <= iters; done += chunk) {
-            e = cudaGraphLaunch(exec, stream);
-            if (e != cudaSuccess) break;
+        if (!slot) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            cudaStream_t rec;
+            NLSB_TRY(internal_stream(&rec));
+            NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
+            enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, &rc);
+            cudaError_t e = cudaStreamEndCapture(rec, &graph);
+            count_launches(0ull - (unsigned long long)chunk);
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+            e = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+            if (victim->exec) cudaGraphExecDestroy(victim->exec);   // released once its in-flight launches complete
+            victim->key = key;
+            victim->exec = exec;
+            slot = victim;
+        }
+        slot->stamp = ++g_graph_stamp;
+        for (; done + chunk <= replayable; done += chunk) {
+            cudaError_t e = cudaGraphLaunch(slot->exec, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
             count_launches((unsigned long long)chunk);
         }
-        cudaGraphExecDestroy(exec);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
     }
-    enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, done, iters - done, stream, &rc);
+    enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, done, iters - done, stream, &rc, diag);
     if (rc) return rc;
     if (iters & 1)
         NLSB_CUDA(cudaMemcpyAsync(psi, work, sizeof(double2) * (size_t)batch * rows * cols, cudaMemcpyDeviceToDevice, stream));
@@ -538,6 +624,24 @@ int nlsb_set_2d_path(int path)
     return 0;
 }
 
+int nlsb_trim_memory(void)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_graph_mutex);
+        for (LoopGraph &g : g_graphs) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = LoopGraph{};
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (int dev = 0; dev < 64; ++dev)
+        if (g_pools[dev]) {
+            cudaError_t e = cudaMemPoolTrimTo(g_pools[dev], 0);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolTrimTo");
+        }
+    return 0;
+}
+
 int nlsb_set_stream_tuning(int sync, int width, int iters_per_cta)
 {
     if (sync < -1 || sync > 1 || width < 0 || iters_per_cta < 0)
@@ -711,6 +815,7 @@ int nlsb_hamiltonian(const double *pumping, const double *coeffs, const double *
                      int klu, int n)
 {
     if (!pumping || !coeffs || !u || !v || !op) return fail(NLSB_EINVAL, "hamiltonian: null argument");
+    NLSB_TRY(check_coeffs(coeffs));
     const int m = 2 * klu + 1;
     NLSB_TRY(check_order_size(n, m));
     std::vector<double> taps((size_t)n * m);
@@ -722,6 +827,7 @@ int nlsb_hamiltonian_2d(const double *pumping, const double *coeffs, const doubl
                         const int *orders, int order, int n)
 {
     if (!pumping || !coeffs || !u || !v || !blocks || !orders) return fail(NLSB_EINVAL, "hamiltonian_2d: null argument");
+    NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     CrossWeights w{};
     NLSB_TRY(blocks_to_weights(n, order, blocks, orders, w.wx, w.wy));
@@ -733,6 +839,7 @@ int nlsb_runge_kutta(double dt, double t0, const double *u0, const double *op, i
 {
     (void)t0;   // the pumping is time independent; the reference advances t but never reads it
     if (!u0 || !op || !u || !pumping || !coeffs || iters < 0) return fail(NLSB_EINVAL, "runge_kutta: bad arguments");
+    NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     std::vector<double> taps((size_t)n * order);
     NLSB_TRY(band_to_taps(n, order, op, taps.data()));
@@ -745,6 +852,7 @@ int nlsb_runge_kutta_2d(double dt, double t0, const double *u0, int n, const dou
     (void)t0;
     if (!u0 || !blocks || !orders || !u || !pumping || !coeffs || iters < 0)
         return fail(NLSB_EINVAL, "runge_kutta_2d: bad arguments");
+    NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     CrossWeights w{};
     NLSB_TRY(blocks_to_weights(n, order, blocks, orders, w.wx, w.wy));
@@ -755,6 +863,7 @@ int nlsb_solve_nls(double dt, double dx, int n, int order, int iters, const doub
                    const double *u0, double *u)
 {
     if (!pumping || !coeffs || !u0 || !u || iters < 0) return fail(NLSB_EINVAL, "solve_nls: bad arguments");
+    NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     std::vector<double> taps((size_t)n * order);
     NLSB_TRY(radial_taps(n, order, dx, taps.data()));
@@ -771,6 +880,7 @@ int nlsb_solve_nls_2d(double dt, double dx, int n, int order, int iters, const d
                       const double *u0, double *u)
 {
     if (!pumping || !coeffs || !u0 || !u || iters < 0) return fail(NLSB_EINVAL, "solve_nls_2d: bad arguments");
+    NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     CrossWeights w{};
     NLSB_TRY(cross_weights(order, dx, w.wx, w.wy));
@@ -781,6 +891,7 @@ int nlsb_chemical_potential_1d(double dx, int n, const double *pumping, const do
                                double *mu)
 {
     if (!pumping || !coeffs || !u0 || !mu) return fail(NLSB_EINVAL, "chemical_potential_1d: null argument");
+    NLSB_TRY(check_coeffs(coeffs));
     const int order = 5;   // hard-wired in the reference (nls.f90:931)
     NLSB_TRY(check_order_size(n, order));
     if (!(dx > 0.0)) return fail(NLSB_EINVAL, "chemical_potential_1d: dx must be positive");
@@ -796,6 +907,7 @@ int nlsb_chemical_potential_2d(double dx, int n, const double *pumping, const do
                                double *mu)
 {
     if (!pumping || !coeffs || !u0 || !mu) return fail(NLSB_EINVAL, "chemical_potential_2d: null argument");
+    NLSB_TRY(check_coeffs(coeffs));
     const int order = 5;   // nls.f90:958
     NLSB_TRY(check_order_size(n, order));
     CrossWeights w{};
@@ -823,6 +935,26 @@ int nlsb_dev_rk4_1d(int batch, int n, int order, int iters, double dt, const dou
     double2 *work;
     NLSB_TRY(mem.alloc(&work, 3 * (size_t)batch * n));
     NLSB_TRY(launch_rk4_1d_staged(batch, n, order, iters, dt, taps, pumping, coeffs, p, work, s));
+    return 0;
+}
+
+int nlsb_dev_rk4_1d_diag(int batch, int n, int order, int iters, double dt, double dx, const double *taps,
+                         const double *pumping, const double *coeffs, double *psi, void *diag_scratch, double *out8,
+                         nlsb_stream_t stream)
+{
+    if (!taps || !pumping || !coeffs || !psi || !diag_scratch || !out8 || batch < 1 || iters < 1 || !(dx > 0.0))
+        return fail(NLSB_EINVAL, "dev_rk4_1d_diag: bad arguments (iters must be >= 1)");
+    NLSB_TRY(check_order_size(n, order));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double2 *p = reinterpret_cast<double2 *>(psi);
+    if (n <= kMaxResident1D) {
+        NLSB_TRY(launch_rk4_1d(batch, n, order, iters, dt, taps, pumping, coeffs, p, s, dx, out8));
+        return 0;
+    }
+    // systems too large for one CTA: the stand-alone reduction on the state entering the last step
+    if (iters > 1) NLSB_TRY(nlsb_dev_rk4_1d(batch, n, order, iters - 1, dt, taps, pumping, coeffs, psi, stream));
+    NLSB_TRY(launch_diagnostics_1d(batch, n, order, dx, taps, pumping, coeffs, p, diag_scratch, out8, s));
+    NLSB_TRY(nlsb_dev_rk4_1d(batch, n, order, 1, dt, taps, pumping, coeffs, psi, stream));
     return 0;
 }
 
@@ -858,6 +990,7 @@ int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double 
 {
     UniformCoeffsScope uniform(shared_coeffs_host);
     if (!pumping || !coeffs || !psi || !workspace || batch < 1 || iters < 0) return fail(NLSB_EINVAL, "dev_rk4_2d: bad arguments");
+    if (shared_coeffs_host) NLSB_TRY(check_coeffs(shared_coeffs_host));
     NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
     if (workspace_bytes < nlsb_dev_rk4_2d_workspace(batch, rows, cols))
         return fail(NLSB_EINVAL, "dev_rk4_2d: workspace of %zu bytes is too small", workspace_bytes);
@@ -868,12 +1001,57 @@ int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double 
     return 0;
 }
 
+size_t nlsb_dev_rk4_2d_diag_scratch(int batch, int rows, int cols, int order)
+{
+    if (batch < 1 || rows < 1 || cols < 1) return 0;
+    size_t bytes = diagnostics_scratch_bytes(batch);
+    const int parts = stream_2d_diag_parts(order, batch, rows, cols);
+    const size_t fused = sizeof(double) * 8 * (size_t)(parts > 0 ? parts : 0) * batch;
+    return (fused > bytes ? fused : bytes) + 256;
+}
+
+int nlsb_dev_rk4_2d_diag(int batch, int rows, int cols, int order, int iters, double dt, double dx, const double *wx,
+                         const double *wy, const double *pumping, const double *coeffs, const double *shared_coeffs_host,
+                         double *psi, void *workspace, size_t workspace_bytes, void *diag_scratch, double *out8,
+                         nlsb_stream_t stream)
+{
+    UniformCoeffsScope uniform(shared_coeffs_host);
+    if (!pumping || !coeffs || !psi || !workspace || !diag_scratch || !out8 || batch < 1 || iters < 1 || !(dx > 0.0))
+        return fail(NLSB_EINVAL, "dev_rk4_2d_diag: bad arguments (iters must be >= 1)");
+    if (shared_coeffs_host) NLSB_TRY(check_coeffs(shared_coeffs_host));
+    NLSB_TRY(check_order_size(rows < cols ? rows : cols, order));
+    if (workspace_bytes < nlsb_dev_rk4_2d_workspace(batch, rows, cols))
+        return fail(NLSB_EINVAL, "dev_rk4_2d_diag: workspace of %zu bytes is too small", workspace_bytes);
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double2 *p = reinterpret_cast<double2 *>(psi);
+    double2 *work = static_cast<double2 *>(workspace);
+    const int path = g_path_2d.load();
+    Fused2DStep probe{batch, rows, cols, 0, rows, 0, rows, p, work, pumping, coeffs, dt, g_uniform_coeffs};
+    const bool fused = (path == 8 || (path == 0 && stream_preferred(order, batch, rows, cols))) && stream_2d_takes(probe) &&
+                       batch <= 32767 * 2;
+    if (fused) {
+        // the reduction rides in the first stage of the last step's launch; a tiny second launch sums the CTAs' partials
+        const DiagRequest req{diag_scratch, dx * dx};
+        NLSB_TRY(enqueue_rk4_2d_fused(batch, rows, cols, order, iters, dt, w, pumping, coeffs, p, work, s, &req));
+        NLSB_TRY(launch_finish_diagnostics(batch, stream_2d_diag_parts(order, batch, rows, cols), diag_scratch, out8, s));
+        return 0;
+    }
+    // kernels without the fused reduction: the stand-alone pass, on the same state (the one entering the last step)
+    if (iters > 1) NLSB_TRY(enqueue_rk4_2d(batch, rows, cols, order, iters - 1, dt, w, pumping, coeffs, p, work, s));
+    NLSB_TRY(launch_diagnostics_2d(batch, rows, cols, order, dx, w, pumping, coeffs, p, diag_scratch, out8, s));
+    NLSB_TRY(enqueue_rk4_2d(batch, rows, cols, order, 1, dt, w, pumping, coeffs, p, work, s));
+    return 0;
+}
+
 int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, const double *wx, const double *wy,
                               int global_row0, int global_rows, int out_row0, int out_row1, const double *pumping,
                               const double *coeffs_host, const double *psi_in, double *psi_out, nlsb_stream_t stream)
 {
     if (!pumping || !coeffs_host || !psi_in || !psi_out || psi_in == psi_out || rows_alloc < 1 || cols < 1)
         return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab: bad arguments");
+    NLSB_TRY(check_coeffs(coeffs_host));
     if (out_row0 < 0 || out_row1 > rows_alloc || out_row0 > out_row1)
         return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab: output rows [%d, %d) outside the slab of %d rows", out_row0,
                     out_row1, rows_alloc);
@@ -897,6 +1075,7 @@ int nlsb_dev_rk4_step_2d_slab_planar(int rows_alloc, int cols, int order, double
 {
     if (!cp || !coeffs_host || !planes_in || !planes_out || planes_in == planes_out || rows_alloc < 1 || cols < 1)
         return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_planar: bad arguments");
+    NLSB_TRY(check_coeffs(coeffs_host));
     if (out_row0 < 0 || out_row1 > rows_alloc || out_row0 > out_row1)
         return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_planar: output rows [%d, %d) outside the slab of %d rows",
                     out_row0, out_row1, rows_alloc);
@@ -1005,6 +1184,13 @@ int nlsb_dev_diagnostics_2d(int batch, int rows, int cols, int order, double dx,
     NLSB_TRY(weights_from_host(order, wx, wy, &w));
     NLSB_TRY(launch_diagnostics_2d(batch, rows, cols, order, dx, w, pumping, coeffs, reinterpret_cast<const double2 *>(psi),
                                    scratch, out8, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int nlsb_dev_divide_check(size_t n, const double *a, const double *b, double *fast, double *exact, nlsb_stream_t stream)
+{
+    if (!a || !b || !fast || !exact) return fail(NLSB_EINVAL, "dev_divide_check: null argument");
+    NLSB_TRY(launch_divide_check(n, a, b, fast, exact, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -15,6 +15,7 @@
 // M = sum w conj(u) u, E = sum w conj(u) v; mu = i E / M.
 
 #include "device_math.cuh"
+#include "diag_acc.cuh"
 #include "kernels.h"
 
 namespace nlsb {
@@ -22,63 +23,20 @@ namespace nlsb {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSums = 6;
+constexpr int kSums = kDiagSums;
+using Acc = DiagAcc;
 
-struct Acc {
-    double s[kSums];     // M_re, M_im, E_re, E_im, damping, particles
-    double m[2];         // max |u|^2, max reservoir
-};
-
-__device__ __forceinline__ Acc acc_zero()
-{
-    Acc a;
-#pragma unroll
-    for (int i = 0; i < kSums; ++i) a.s[i] = 0.0;
-    a.m[0] = a.m[1] = 0.0;
-    return a;
-}
-
-__device__ __forceinline__ Acc warp_reduce(Acc a)
-{
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-        for (int i = 0; i < kSums; ++i) a.s[i] += __shfl_down_sync(0xffffffffu, a.s[i], off);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) a.m[i] = fmax(a.m[i], __shfl_down_sync(0xffffffffu, a.m[i], off));
-    }
-    return a;
-}
+__device__ __forceinline__ Acc acc_zero() { return diag_zero(); }
 
 __device__ __forceinline__ Acc block_reduce(Acc a)
 {
     __shared__ Acc part[kThreads / 32];
-    a = warp_reduce(a);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) part[warp] = a;
-    __syncthreads();
-    Acc t = acc_zero();
-    if (warp == 0) {
-        if (lane < kThreads / 32) t = part[lane];
-        t = warp_reduce(t);
-    }
-    return t;   // valid in thread 0
+    return diag_block_reduce(a, part);   // valid in thread 0
 }
 
-// One node's contribution: u the field, v = H(u), w the weight of the dot products, wd the area element.
 __device__ __forceinline__ void accumulate(Acc &a, const RhsCoeffs &c, double cp, double2 u, double2 v, double w, double wd)
 {
-    const double ur = u.x * w, ui = u.y * w, vr = v.x * w, vi = v.y * w;     // conj(u) * (x * w), as reduce.cu
-    a.s[0] += u.x * ur + u.y * ui;
-    a.s[1] += u.x * ui - u.y * ur;
-    a.s[2] += u.x * vr + u.y * vi;
-    a.s[3] += u.x * vi - u.y * vr;
-    const double usq = u.x * u.x + u.y * u.y;
-    const double res = cp / (c.c13 + c.c14 * usq);                             // getReservoir, nls/model.py:376-380
-    a.s[4] += (res - 1.0) * usq * wd;
-    a.s[5] += usq * wd;
-    a.m[0] = fmax(a.m[0], usq);
-    a.m[1] = fmax(a.m[1], res);
+    diag_accumulate(a, c, cp, u, v, w, wd);
 }
 
 // A CTA's reduced sums: a partial for the finishing launch, or -- when the member has a single CTA -- the result.
@@ -235,6 +193,14 @@ WeightsK<K> pack(const CrossWeights &w)
 }
 
 }  // namespace
+
+// Sum `parts` partials per member in a fixed order (second pass of every diagnostics reduction).
+int launch_finish_diagnostics(int batch, int parts, const void *partial, double *out8, cudaStream_t stream)
+{
+    finish_diagnostics_kernel<<<(unsigned)batch, kThreads, 0, stream>>>(parts, static_cast<const Acc *>(partial), out8);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
 
 size_t diagnostics_scratch_bytes(int batch) { return sizeof(Acc) * 592 * (size_t)(batch > 0 ? batch : 1); }
 

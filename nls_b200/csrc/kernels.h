@@ -13,8 +13,10 @@ enum StageMode { kStageRhs = 0, kStageFirst = 1, kStageMid = 2, kStageLast = 3 }
 
 // kernels_1d.cu
 constexpr int kMaxResident1D = 2048;   // largest n the CTA-resident 1D kernel handles (8 nodes x 256 threads)
+// diag_out8 non-null (and iters >= 1): the launch also writes the 8 scalar diagnostics per member (diag_acc.cuh) of
+// the state ENTERING its last step, reduced inside that step's first stage; dx is the radial step of their weights
 int launch_rk4_1d(int batch, int n, int order, int iters, double dt, const double *taps, const double *pumping,
-                  const double *coeffs, double2 *psi, cudaStream_t stream);
+                  const double *coeffs, double2 *psi, cudaStream_t stream, double dx = 0.0, double *diag_out8 = nullptr);
 // n > kMaxResident1D: per-stage launches through global memory; work holds 3*batch*n complex values
 int launch_rk4_1d_staged(int batch, int n, int order, int iters, double dt, const double *taps,
                          const double *pumping, const double *coeffs, double2 *psi, double2 *work,
@@ -49,6 +51,10 @@ struct Fused2DStep {
     const double *coeffs;    // [batch][23] on the device
     double dt;
     const RhsCoeffs *uniform;   // host: non-null when every member shares these coefficients
+    // strip-marching kernel only: when non-null the step also reduces the scalar diagnostics of the state it reads
+    // (`in`) into [batch][stream_2d_diag_parts] partial sums (diag_acc.cuh), area element diag_area
+    void *diag_partial = nullptr;
+    double diag_area = 0.0;
 };
 // variant 0: 32x32 tiles, two CTAs per SM; variant 1: 32x64 tiles, one CTA of 512 threads per SM
 int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
@@ -56,7 +62,10 @@ int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const
 // and writes interleaved psi (grids with an odd number of columns are handed to the tile kernel: same bits).
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);
 int stream_2d_plan(int order, int batch, int out_rows, int cols, int *threads, int *strips, int *chunk_rows);
+bool stream_2d_takes(const Fused2DStep &s);
+int stream_2d_diag_parts(int order, int batch, int out_rows, int cols);
 void stream_2d_set_tuning(int sync, int width, int iters);
+void stream_2d_get_tuning(int *t3);
 // resident_2d.cu: `steps` RK4 steps of a SMALL grid in one cooperative launch, psi updated in place; the field
 // lives in registers (one patch per CTA), neighbouring CTAs exchange edge nodes through `mailbox` (device scratch
 // of the size resident_2d_query reports, zero-filled before its first use).  Packets carry sequence numbers
@@ -113,6 +122,7 @@ int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w,
                            double sign, cudaStream_t stream);
 // diagnostics.cu: fused scalar diagnostics of device-resident states (8 doubles per member, see nls_b200.h)
 size_t diagnostics_scratch_bytes(int batch);
+int launch_finish_diagnostics(int batch, int parts, const void *partial, double *out8, cudaStream_t stream);
 int launch_diagnostics_2d(int batch, int rows, int cols, int order, double dx, const CrossWeights &w,
                           const double *pumping, const double *coeffs, const double2 *u, void *scratch, double *out8,
                           cudaStream_t stream);
@@ -121,6 +131,7 @@ int launch_diagnostics_1d(int batch, int n, int order, double dx, const double *
 // pumping_gen.cu: profiles of an ensemble generated on the device; params_dev: [batch][5] on the device
 int launch_pumping_profiles(int dim, int kind, int batch, int n, double dx, const double *params_dev, double *out,
                             cudaStream_t stream);
+int launch_divide_check(size_t n, const double *a, const double *b, double *fast, double *exact, cudaStream_t stream);
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,
                      cudaStream_t stream);
 

@@ -14,6 +14,7 @@
 // u + (k1 + 2 k2 + 2 k3 + k4)*dt/6.
 
 #include "device_math.cuh"
+#include "diag_acc.cuh"
 #include "kernels.h"
 
 namespace nlsb {
@@ -24,10 +25,15 @@ constexpr int kResidentThreads = 256;   // 255 registers per thread available: t
 
 // MINBLOCKS = 2 (<= 128 registers, two CTAs per SM) feeds the FP64 pipe better when an ensemble fills
 // the GPU; a lone system runs faster with all 255 registers (MINBLOCKS = 1, no spills).
-template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS>
+//
+// DIAG: the first stage of the LAST step holds k1 = H(psi) of the state entering that step; its scalar diagnostics
+// (diag_acc.cuh: chemical-potential sums with weight r = i dx, damping integral and particle number with the area
+// element 2 pi r dx on the reference's linspace grid, peak density / reservoir) are reduced there and written to
+// out8[member] -- the convergence loop of tools/check.py without a second pass over the field.
+template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS, bool DIAG>
 __global__ void __launch_bounds__(kResidentThreads, MINBLOCKS)
 rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, const double *__restrict__ pumping,
-                const double *__restrict__ coeffs, double2 *__restrict__ psi)
+                const double *__restrict__ coeffs, double2 *__restrict__ psi, double dx, double *__restrict__ out8)
 {
     constexpr int K = (M - 1) / 2;
     static_assert(PPT >= K, "a thread must own at least K nodes so halos come from adjacent threads only");
@@ -67,6 +73,8 @@ rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, co
     }
 
     const double half_dt = dt / 2, dt6 = dt / 6;
+    DiagAcc dacc = diag_zero();
+    const double ring = n > 1 ? (n * dx) / (n - 1) : 0.0;              // spacing of linspace(0, n dx, n)
 
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -100,6 +108,11 @@ rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, co
                 }
                 double2 k = rhs_point(c, cp[p], w[K + p], lr, li);
                 if (!live[p]) k = make_double2(0.0, 0.0);
+                if (DIAG && s == 0 && it == iters - 1 && live[p]) {
+                    const int i = i0 + p;
+                    diag_accumulate(dacc, c, cp[p], w[K + p], k, ((double)(i + 1) - 1.0) * dx,      // nls.f90:940-947
+                                    6.283185307179586 * (i * ring) * dx);                           // nls/model.py:357-361
+                }
                 if (s == 0) {
                     acc[p] = k;
                     y[p].x = fma(k.x, half_dt, u[p].x);
@@ -126,6 +139,17 @@ rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, co
 #pragma unroll
     for (int p = 0; p < PPT; ++p)
         if (live[p]) u_g[i0 + p] = u[p];
+    if (DIAG) {
+        __syncthreads();                      // the halo buffers are free: stage them for the block reduction
+        const DiagAcc total = diag_block_reduce(dacc, reinterpret_cast<DiagAcc *>(halo));
+        if (tid == 0) {
+            double *o = out8 + member * 8;
+#pragma unroll
+            for (int i = 0; i < kDiagSums; ++i) o[i] = total.s[i];
+            o[6] = total.m[0];
+            o[7] = total.m[1];
+        }
+    }
 }
 
 template <int M>
@@ -134,8 +158,8 @@ __global__ void hamiltonian_1d_kernel(int n, const double *__restrict__ taps, co
                                       double2 *__restrict__ v)
 {
     constexpr int K = (M - 1) / 2;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t member = blockIdx.y;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;    // members on grid.x (no 65535 limit), node blocks on grid.y
+    const size_t member = blockIdx.x;
     if (i >= n) return;
     const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
     const double2 *um = u + member * n;
@@ -162,8 +186,8 @@ __global__ void stage_1d_kernel(int n, int mode, const double *__restrict__ taps
                                 double2 *__restrict__ ydst, double cy, double dt6)
 {
     constexpr int K = (M - 1) / 2;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t member = blockIdx.y;
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;    // members on grid.x (no 65535 limit), node blocks on grid.y
+    const size_t member = blockIdx.x;
     if (i >= n) return;
     const size_t g = member * n + i;
     const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
@@ -210,46 +234,56 @@ __global__ void band_matvec_1d_kernel(int n, const double *__restrict__ taps, co
     u[i] = fma(sign, s, u[i]);
 }
 
-template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS>
-int launch_resident(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
-                    const double *coeffs, double2 *psi, cudaStream_t stream)
+template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS, bool DIAG>
+int launch_resident_d(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
+                      const double *coeffs, double2 *psi, double dx, double *out8, cudaStream_t stream)
 {
     constexpr int K = (M - 1) / 2;
     int threads = (n + PPT - 1) / PPT;
     threads = (threads + 31) / 32 * 32;
-    const size_t smem = sizeof(double2) * 2 * 2 * K * (threads + 2);
-    cudaError_t e = cudaFuncSetAttribute(rk4_1d_resident<M, PPT, TAPS_IN_REGS, MINBLOCKS>,
+    size_t smem = sizeof(double2) * 2 * 2 * K * (threads + 2);
+    if (DIAG && smem < sizeof(DiagAcc) * (kResidentThreads / 32)) smem = sizeof(DiagAcc) * (kResidentThreads / 32);
+    cudaError_t e = cudaFuncSetAttribute(rk4_1d_resident<M, PPT, TAPS_IN_REGS, MINBLOCKS, DIAG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    rk4_1d_resident<M, PPT, TAPS_IN_REGS, MINBLOCKS><<<batch, threads, smem, stream>>>(n, iters, dt, taps, pumping,
-                                                                                      coeffs, psi);
+    rk4_1d_resident<M, PPT, TAPS_IN_REGS, MINBLOCKS, DIAG><<<batch, threads, smem, stream>>>(n, iters, dt, taps, pumping,
+                                                                                            coeffs, psi, dx, out8);
     count_launches(1);
     return (int)cudaGetLastError();
 }
 
+template <int M, int PPT, bool TAPS_IN_REGS, int MINBLOCKS>
+int launch_resident(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
+                    const double *coeffs, double2 *psi, double dx, double *out8, cudaStream_t stream)
+{
+    if (out8 && iters > 0)
+        return launch_resident_d<M, PPT, TAPS_IN_REGS, MINBLOCKS, true>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
+    return launch_resident_d<M, PPT, TAPS_IN_REGS, MINBLOCKS, false>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
+}
+
 template <int M>
 int launch_resident_m(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
-                      const double *coeffs, double2 *psi, cudaStream_t stream)
+                      const double *coeffs, double2 *psi, double dx, double *out8, cudaStream_t stream)
 {
     if (n <= 4 * kResidentThreads) {
         if (M <= 5 && batch >= 2 * 148)   // enough members for two CTAs on every SM
-            return launch_resident<M, 4, true, (M <= 5) ? 2 : 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
-        return launch_resident<M, 4, true, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
+            return launch_resident<M, 4, true, (M <= 5) ? 2 : 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
+        return launch_resident<M, 4, true, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
     }
-    return launch_resident<M, 8, false, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
+    return launch_resident<M, 8, false, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
 }
 
 }  // namespace
 
 int launch_rk4_1d(int batch, int n, int order, int iters, double dt, const double *taps, const double *pumping,
-                  const double *coeffs, double2 *psi, cudaStream_t stream)
+                  const double *coeffs, double2 *psi, cudaStream_t stream, double dx, double *diag_out8)
 {
     if (n > kMaxResident1D)
         return fail(NLSB_ESIZE, "resident 1D kernel handles n <= %d (n = %d): use launch_rk4_1d_staged", kMaxResident1D, n);
     switch (order) {
-    case 3: return launch_resident_m<3>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
-    case 5: return launch_resident_m<5>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
-    case 7: return launch_resident_m<7>(batch, n, iters, dt, taps, pumping, coeffs, psi, stream);
+    case 3: return launch_resident_m<3>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, diag_out8, stream);
+    case 5: return launch_resident_m<5>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, diag_out8, stream);
+    case 7: return launch_resident_m<7>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, diag_out8, stream);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
 }
@@ -261,7 +295,7 @@ int launch_rk4_1d_staged(int batch, int n, int order, int iters, double dt, cons
     if (order != 3 && order != 5 && order != 7) return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
     const size_t np = (size_t)batch * n;
     double2 *ya = work, *yb = work + np, *acc = work + 2 * np;
-    const dim3 block(128), grid((n + 127) / 128, batch);
+    const dim3 block(128), grid(batch, (n + 127) / 128);
     auto stage = [&](int mode, const double2 *ysrc, double2 *ydst, double cy) {
         switch (order) {
         case 3: stage_1d_kernel<3><<<grid, block, 0, stream>>>(n, mode, taps, pumping, coeffs, ysrc, psi, acc, ydst, cy, dt / 6); break;
@@ -282,7 +316,7 @@ int launch_rk4_1d_staged(int batch, int n, int order, int iters, double dt, cons
 int launch_hamiltonian_1d(int batch, int n, int order, const double *taps, const double *pumping,
                           const double *coeffs, const double2 *u, double2 *v, cudaStream_t stream)
 {
-    const dim3 block(128), grid((n + 127) / 128, batch);
+    const dim3 block(128), grid(batch, (n + 127) / 128);
     switch (order) {
     case 3: hamiltonian_1d_kernel<3><<<grid, block, 0, stream>>>(n, taps, pumping, coeffs, u, v); break;
     case 5: hamiltonian_1d_kernel<5><<<grid, block, 0, stream>>>(n, taps, pumping, coeffs, u, v); break;

@@ -172,6 +172,25 @@ int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w,
     return (int)cudaGetLastError();
 }
 
+// Self-test of the divide every fused kernel uses: quotients by div_fast (device_math.cuh) and by the correctly
+// rounded IEEE divide, element by element, for the parity tests.
+__global__ void divide_check_kernel(size_t n, const double *__restrict__ a, const double *__restrict__ b,
+                                    double *__restrict__ fast, double *__restrict__ exact)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        fast[i] = div_fast(a[i], b[i]);
+        exact[i] = __ddiv_rn(a[i], b[i]);
+    }
+}
+
+int launch_divide_check(size_t n, const double *a, const double *b, double *fast, double *exact, cudaStream_t stream)
+{
+    if (n == 0) return 0;
+    divide_check_kernel<<<148 * 8, 256, 0, stream>>>(n, a, b, fast, exact);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
 int launch_reservoir(size_t npts, RhsCoeffs c, const double *pumping, const double *u_sqr, double *r,
                      cudaStream_t stream)
 {

@@ -48,6 +48,8 @@ struct StreamArgs {
     const double *coeffs;    // [batch][23] -- unused when UNIFORM
     RhsCoeffs cu;
     double dt;
+    DiagAcc *diag;           // DIAG: [batch][CTAs per member] partial sums of the entering state's diagnostics
+    double area;             // DIAG: area element dx^2
 };
 
 template <int K>
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *map, uint3
 // 2-4 (9-14 % slower: the stage 2-4 loads can then no longer be hoisted above the stage-1 arithmetic).
 enum StreamSync { kSyncEvery = 0, kSyncPair = 1 };
 
-template <typename C, bool UNIFORM, int SYNC>
+template <typename C, bool UNIFORM, int SYNC, bool DIAG>
 __global__ void __launch_bounds__(C::T, C::CTAS_PER_SM)
 rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ StreamWeights<C::K> wa,
                   const __grid_constant__ TensorMap map, const __grid_constant__ TensorMap map_p)
@@ -145,6 +147,7 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
     __syncthreads();
 
     State<C> s;
+    DiagAcc dacc = diag_zero();
     mbar_wait(bar0, 0);
     march_begin<C>(s, L, g);
 
@@ -159,7 +162,7 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
                 const int b = (it + 2 * K) / RB;
                 mbar_wait(bar0 + 8 * (b % NB), (b / NB) & 1);
             }
-            march_iter<C>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_);
+            march_iter<C, DIAG>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_, &dacc, a.area);
             if ((ph + 1) % PERIOD == 0) {
                 __syncthreads();
                 // thread 0 re-requests the batches whose last reader was one of the iterations this barrier closes:
@@ -176,6 +179,12 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
         }
         const double2 *t = rh; rh = ro; ro = t;
         const double *tp = ph_; ph_ = po_; po_ = tp;
+    }
+    if (DIAG) {
+        // one partial per CTA, reduced in a fixed order (the stage rings are free now: the march is over)
+        __syncthreads();
+        const DiagAcc total = diag_block_reduce(dacc, reinterpret_cast<DiagAcc *>(smem_raw));
+        if (tid == 0) a.diag[member * gridDim.x + blockIdx.x] = total;
     }
 }
 
@@ -253,7 +262,7 @@ int cached_map(const MapKey &key, TensorMap *out)
     return 0;
 }
 
-template <typename C, bool UNIFORM, int SYNC>
+template <typename C, bool UNIFORM, int SYNC, bool DIAG>
 int configure_stream()
 {
     static bool configured[64] = {};
@@ -261,9 +270,9 @@ int configure_stream()
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
@@ -289,10 +298,12 @@ int sm_count()
 //   worth about 8), and CTAs run in waves of (SMs x CTAs per SM).
 // The planner minimises   waves x (iterations per CTA + 8) x (time of one iteration of a full SM)   over the
 // compiled widths and the chunk lengths.  The time of an iteration of a full SM is T x CTAs-per-SM x shape_cost(T):
-// two 128-thread CTAs per SM overlap each other's load bursts and barriers and need 8.5 % less time per thread than
-// one 256-thread CTA (measured on B200, order 5, 8192^2 and 32 x 1024^2, profiles/r2_stream_sync_sweep.jsonl;
-// 160 / 192 / 224-thread strips were measured too and dropped: a CTA whose warps do not divide evenly over the four
-// schedulers runs at the pace of the fullest one -- 224 threads take as long per iteration as 256).
+// two 128-thread CTAs per SM overlap each other's load bursts and barriers and need less time per thread than one
+// 256-thread CTA -- 8.5 % less in 30-step bursts at 1965 MHz, 3-5 % less in second-long runs, where this kernel sits
+// at the 1000 W power cap (1.75-1.80 GHz) and every redundantly swept column costs energy (measured on B200, order
+// 5, 8192^2 and 32..64 x 1024^2: profiles/r2_stream_sync_sweep.jsonl, r2_stream_sustained.jsonl; the sustained figure
+// is the one used).  160 / 192 / 224-thread strips were measured too and dropped: a CTA whose warps do not divide
+// evenly over the four schedulers runs at the pace of the fullest one -- 224 threads take as long per iteration as 256.
 struct StreamPlan {
     int threads, strips, chunk_rows, sync;
     double cost;
@@ -300,7 +311,7 @@ struct StreamPlan {
 
 inline double shape_cost(int K, int T)
 {
-    if (K == 2 && T == 128) return 0.915;
+    if (K == 2 && T == 128) return 0.96;
     if (K == 1 && T == 128) return 1.03;
     return 1.0;
 }
@@ -331,10 +342,10 @@ StreamPlan plan_shape(int out_rows, int cols, int batch)
     return p;
 }
 
-template <typename C, bool UNIFORM, int SYNC>
+template <typename C, bool UNIFORM, int SYNC, bool DIAG>
 int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
-    int rc = configure_stream<C, UNIFORM, SYNC>();
+    int rc = configure_stream<C, UNIFORM, SYNC, DIAG>();
     if (rc) return rc;
     const int out_rows = s.out_row1 - s.out_row0;
     StreamArgs a{};
@@ -345,6 +356,8 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
     a.out = s.out; a.coeffs = s.coeffs;
     if (UNIFORM) a.cu = *s.uniform;
     a.dt = s.dt;
+    a.diag = static_cast<DiagAcc *>(s.diag_partial);
+    a.area = s.diag_area;
     StreamWeights<C::K> wa;
     for (int i = 0; i < C::NW; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
     TensorMap map, map_p;
@@ -354,7 +367,7 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
     if (rc) return rc;
     const int chunks = (out_rows + a.chunk_rows - 1) / a.chunk_rows;
     const dim3 grid((unsigned)(a.strips * chunks), (unsigned)s.batch);
-    rk4_stream_kernel<C, UNIFORM, SYNC><<<grid, C::T, C::SMEM, stream>>>(a, wa, map, map_p);
+    rk4_stream_kernel<C, UNIFORM, SYNC, DIAG><<<grid, C::T, C::SMEM, stream>>>(a, wa, map, map_p);
     count_launches(1);
     return (int)cudaGetLastError();
 }
@@ -362,9 +375,14 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
 template <typename C>
 int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
+    if (s.diag_partial)     // the diagnostics-carrying step of a chunk (one launch in many): a single flavour
+        return s.uniform ? launch_stream_sync<C, true, kSyncEvery, true>(s, w, p, stream)
+                         : launch_stream_sync<C, false, kSyncEvery, true>(s, w, p, stream);
     if (p.sync == kSyncPair)
-        return s.uniform ? launch_stream_sync<C, true, kSyncPair>(s, w, p, stream) : launch_stream_sync<C, false, kSyncPair>(s, w, p, stream);
-    return s.uniform ? launch_stream_sync<C, true, kSyncEvery>(s, w, p, stream) : launch_stream_sync<C, false, kSyncEvery>(s, w, p, stream);
+        return s.uniform ? launch_stream_sync<C, true, kSyncPair, false>(s, w, p, stream)
+                         : launch_stream_sync<C, false, kSyncPair, false>(s, w, p, stream);
+    return s.uniform ? launch_stream_sync<C, true, kSyncEvery, false>(s, w, p, stream)
+                     : launch_stream_sync<C, false, kSyncEvery, false>(s, w, p, stream);
 }
 
 // Strip widths the march is compiled for (order 7 has one: rings of 256 columns exceed 227 KB of shared memory and
@@ -412,6 +430,13 @@ int launch_stream_order(const Fused2DStep &s, const CrossWeights &w, cudaStream_
 
 }  // namespace
 
+void stream_2d_get_tuning(int *t3)
+{
+    t3[0] = g_tune_sync.load();
+    t3[1] = g_tune_width.load();
+    t3[2] = g_tune_iters.load();
+}
+
 void stream_2d_set_tuning(int sync, int width, int iters)
 {
     g_tune_sync.store(sync);
@@ -431,6 +456,20 @@ int stream_2d_plan(int order, int batch, int out_rows, int cols, int *threads, i
     }
     *threads = p.threads; *strips = p.strips; *chunk_rows = p.chunk_rows;
     return 0;
+}
+
+// Whether launch_rk4_step_stream_2d runs the strip-marching kernel for this step (else it hands over to the tile kernel).
+bool stream_2d_takes(const Fused2DStep &s)
+{
+    return (s.cols & 1) == 0 && (reinterpret_cast<uintptr_t>(s.pumping) & 15) == 0;
+}
+
+// CTAs per member of the launch = partial sums per member a diagnostics-carrying step writes.
+int stream_2d_diag_parts(int order, int batch, int out_rows, int cols)
+{
+    int threads = 0, strips = 0, chunk_rows = 0;
+    if (stream_2d_plan(order, batch, out_rows, cols, &threads, &strips, &chunk_rows) || chunk_rows <= 0) return 0;
+    return strips * ((out_rows + chunk_rows - 1) / chunk_rows);
 }
 
 int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)

@@ -31,6 +31,7 @@
 #pragma once
 
 #include "device_math.cuh"
+#include "diag_acc.cuh"
 
 #define NLSB_HD __host__ __device__ __forceinline__
 
@@ -210,10 +211,14 @@ NLSB_HD const E *ring_row(const E *rh, const E *ro, int srel)
 // One iteration of the march.  `ph` must equal it mod U, rh / ro are the halves of the psi ring and ph_ / po_ of
 // the pumping ring (already offset to this thread's column) as ring_row wants them; in the kernel `ph` is a
 // compile-time constant of the unrolled copy and the halves swap once per unrolled body.
-template <class C>
+//
+// DIAG: stage 1 holds k1 = H(psi) of the state ENTERING the step, so the scalar diagnostics of that state (chemical
+// potential sums, damping integral, particle number, peak density / reservoir: diag_acc.cuh) are accumulated there
+// for the nodes this CTA produces -- no extra pass over the field, no stencil evaluated twice.
+template <class C, bool DIAG = false>
 NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const RhsCoeffs &c, const double (&wx)[C::NW],
                         const double (&wy)[C::NW], int it, int ph, const double2 *rh, const double2 *ro, const double *ph_,
-                        const double *po_)
+                        const double *po_, DiagAcc *diag = nullptr, double area = 0.0)
 {
     constexpr int K = C::K, U = C::U, NW = C::NW, YP = C::YP;
     const int j = g.jstart + it;
@@ -250,6 +255,10 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         double lr, li;
         cross_stencil<C, U>(s.psi, ci, x1, wx, wy, lr, li);
         const double2 k = rhs_point(c, s.cp[ci], u, lr, li);
+        if (DIAG) {
+            if (L.col_owned && (unsigned)(j - g.r0) < (unsigned)(g.r1 - g.r0) && row_in_domain(L, j))
+                diag_accumulate(*diag, c, s.cp[ci], u, k, 1.0, area);
+        }
         double2 y;
         y.x = in1 ? fma(k.x, L.half_dt, u.x) : 0.0;
         y.y = in1 ? fma(k.y, L.half_dt, u.y) : 0.0;

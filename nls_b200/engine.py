@@ -70,6 +70,11 @@ def _coeff_table(coeffs, batch):
         c = np.broadcast_to(c, (batch, 23))
     if c.shape != (batch, 23):
         raise ValueError("coeffs must have shape (23,) or (batch, 23); got %r" % (c.shape,))
+    used = c[:, [2, 3, 4, 5, 11, 12, 13]]
+    if not np.isfinite(used).all() or not (c[:, 12] > 0).all() or not (c[:, 13] >= 0).all():
+        # precondition of the kernels' divide (csrc/device_math.cuh); the C ABI checks the same for host tables
+        raise ValueError("coeffs: the entries read by the right-hand side must be finite, coeffs[12] > 0 and coeffs[13] >= 0 "
+                         "(the reservoir denominator c13 + c14 |psi|^2 must stay positive)")
     return np.array(c, dtype=np.float64, order="C", copy=True)
 
 
@@ -111,20 +116,21 @@ def _diagnostics_dict(out8):
 
 
 def _advance_until(engine, rel_tol, check_every, max_iters, quantity):
-    """Shared body of ``advance_until``: chunks of ``check_every`` steps, one device-side reduction per chunk."""
+    """Shared body of ``advance_until``: chunks of ``check_every`` steps; the reduction rides inside the last launch of
+    every chunk (``advance(chunk, diagnostics=True)``: the state one step before the chunk's end), so the field is
+    read once per step and nothing but 8 doubles per member is copied back per chunk."""
     if check_every < 1 or max_iters < 0:
         raise ValueError("check_every must be positive and max_iters non-negative")
-    previous = engine.diagnostics()[quantity]
-    done, history = 0, [previous]
+    previous, done, history = None, 0, []
     while done < max_iters:
         chunk = min(int(check_every), int(max_iters) - done)
-        engine.advance(chunk)
+        current = engine.advance(chunk, diagnostics=True)[quantity]
         done += chunk
-        current = engine.diagnostics()[quantity]
         history.append(current)
-        change = np.max(np.abs(current - previous) / np.maximum(np.abs(current), np.finfo(float).tiny))
-        if change <= rel_tol:
-            return done, True, history
+        if previous is not None:
+            change = np.max(np.abs(current - previous) / np.maximum(np.abs(current), np.finfo(float).tiny))
+            if change <= rel_tol:
+                return done, True, history
         previous = current
     return done, False, history
 
@@ -156,13 +162,27 @@ class Ensemble1D(object):
             raise ValueError("expected shape (%d, %d), got %r" % (self.batch, self.n, tuple(t.shape)))
         return t
 
-    def advance(self, iters):
-        """``iters`` RK4 steps of every member, in place, asynchronously on the current stream."""
+    def advance(self, iters, diagnostics=False):
+        """``iters`` RK4 steps of every member, in place, asynchronously on the current stream; returns self.
+
+        diagnostics=True (iters >= 1): the same steps, and the scalar diagnostics (as ``diagnostics()``) of the state
+        ENTERING the last step -- step ``steps_done - 1`` after the call -- are reduced inside that step's launch
+        (its first stage holds H(psi) of that state; C ABI nlsb_dev_rk4_1d_diag).  Returns the dictionary, with the
+        step index under ``"step"``; reading it synchronises."""
         with torch.cuda.device(self.device):
-            _lib.call("nlsb_dev_rk4_1d", self.batch, self.n, self.order, int(iters), self.dt, _dptr(self.taps),
-                      _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi), _stream())
+            if not diagnostics:
+                _lib.call("nlsb_dev_rk4_1d", self.batch, self.n, self.order, int(iters), self.dt, _dptr(self.taps),
+                          _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi), _stream())
+                self.steps_done += int(iters)
+                return self
+            out = torch.empty((self.batch, 8), dtype=torch.float64, device=self.device)
+            scratch = torch.empty(_lib.load().nlsb_dev_diagnostics_scratch(self.batch), dtype=torch.uint8, device=self.device)
+            _lib.call("nlsb_dev_rk4_1d_diag", self.batch, self.n, self.order, int(iters), self.dt, self.dx, _dptr(self.taps),
+                      _dptr(self.pumping), _dptr(self.coeffs), _dptr(self.psi), _dptr(scratch), _dptr(out), _stream())
         self.steps_done += int(iters)
-        return self
+        result = _diagnostics_dict(out)
+        result["step"] = self.steps_done - 1
+        return result
 
     def hamiltonian(self, u=None):
         u = self.psi if u is None else _to_device(u, torch.complex128, self.device)
@@ -227,6 +247,7 @@ class Grid2D(object):
             self.psi = self._field(u0, torch.complex128)
             nbytes = _lib.load().nlsb_dev_rk4_2d_workspace(self.batch, self.rows, self.cols)
             self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._diag_scratch = None
         self.steps_done = 0
 
     def _field(self, value, dtype):
@@ -243,14 +264,31 @@ class Grid2D(object):
     def _w(self, a):
         return a.ctypes.data_as(C.c_void_p)
 
-    def advance(self, iters):
+    def advance(self, iters, diagnostics=False):
+        """``iters`` RK4 steps of every member, in place, asynchronously on the current stream; returns self.
+
+        diagnostics=True (iters >= 1): as ``Ensemble1D.advance`` -- the diagnostics of the state entering the last
+        step, reduced inside that step's launch by the strip-marching kernel (C ABI nlsb_dev_rk4_2d_diag; kernels
+        without the fused reduction run the stand-alone pass before their last step: same numbers)."""
+        shared = self._w(self.shared_coeffs) if self.shared_coeffs is not None else None
         with torch.cuda.device(self.device):
-            _lib.call("nlsb_dev_rk4_2d", self.batch, self.rows, self.cols, self.order, int(iters), self.dt,
-                      self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs),
-                      self._w(self.shared_coeffs) if self.shared_coeffs is not None else None, _dptr(self.psi),
-                      _dptr(self.workspace), C.c_size_t(self.workspace.numel()), _stream())
+            if not diagnostics:
+                _lib.call("nlsb_dev_rk4_2d", self.batch, self.rows, self.cols, self.order, int(iters), self.dt,
+                          self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), shared, _dptr(self.psi),
+                          _dptr(self.workspace), C.c_size_t(self.workspace.numel()), _stream())
+                self.steps_done += int(iters)
+                return self
+            out = torch.empty((self.batch, 8), dtype=torch.float64, device=self.device)
+            if self._diag_scratch is None:
+                nbytes = _lib.load().nlsb_dev_rk4_2d_diag_scratch(self.batch, self.rows, self.cols, self.order)
+                self._diag_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.call("nlsb_dev_rk4_2d_diag", self.batch, self.rows, self.cols, self.order, int(iters), self.dt, self.dx,
+                      self._w(self.wx), self._w(self.wy), _dptr(self.pumping), _dptr(self.coeffs), shared, _dptr(self.psi),
+                      _dptr(self.workspace), C.c_size_t(self.workspace.numel()), _dptr(self._diag_scratch), _dptr(out), _stream())
         self.steps_done += int(iters)
-        return self
+        result = _diagnostics_dict(out)
+        result["step"] = self.steps_done - 1
+        return result
 
     def hamiltonian(self, u=None):
         u = self.psi if u is None else _to_device(u, torch.complex128, self.device)

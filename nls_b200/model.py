@@ -86,10 +86,12 @@ class Problem(object):
             originals.setdefault(key, value)
         kwargs["original_params"] = originals
 
-        kind = kwargs["model"]
-        if kind in ("1d", "default", str(Model1D)):
+        # .mat files store str(type(model)) (ref model.py:265): accept this package's class strings and the
+        # reference's ("<class 'nls.model.Model1D'>") alike, so that the reference's own checkpoints restore
+        kind = str(kwargs["model"]).strip()
+        if kind in ("1d", "default") or kind.rstrip("'>").endswith("Model1D"):
             return self.fabricateModel1D(*args, **kwargs)
-        if kind in ("2d", str(Model2D)):
+        if kind == "2d" or kind.rstrip("'>").endswith("Model2D"):
             return self.fabricateModel2D(*args, **kwargs)
         raise Exception("Unknown model passed!")
 

@@ -554,6 +554,23 @@ class SlabGrid2D(object):
             raise RuntimeError("set_local_state between two halo exchanges")
         self.psi[self.cur].copy_(other_buffer)
 
+    def upload(self, pumping_local, psi_local):
+        """Load this rank's slab from HOST arrays of the local layout (rows_alloc x n, halo rows included; pinned
+        memory makes the copies asynchronous): the end-to-end path of bench.py.  Only valid right after an exchange."""
+        if self.since_exchange != 0:
+            raise RuntimeError("upload between two halo exchanges")
+        if self.planar:
+            raise NotImplementedError("upload is implemented for interleaved slabs")
+        self.pumping.copy_(pumping_local, non_blocking=True)
+        self.psi[self.cur].copy_(psi_local, non_blocking=True)
+        return self
+
+    def download(self, out_host):
+        """Copy the owned rows of the current state to a HOST array (rows_local x n) and wait for it."""
+        out_host.copy_(self.local_solution(), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
+
     def close(self):
         """Release peer mappings and graphs (call on every rank before the process group is destroyed)."""
         self.graphs = {}

@@ -46,6 +46,51 @@ def _coeffs(c):
     return c
 
 
+def _same_shape(what, ref_name, ref, **arrays):
+    """f2py checks every array extent against the inferred n (``check(shape(pumping,0)==n)``) and raises; the C ABI
+    takes raw pointers, so the same check happens here before anything is handed over."""
+    for name, a in arrays.items():
+        if a.shape != ref.shape:
+            raise ValueError("%s: %s has shape %r but %s has shape %r" % (what, name, a.shape, ref_name, ref.shape))
+
+
+def _band(op, what, n, klu=None):
+    """A band matrix (2 klu + 1, n) in BLAS GB storage; returns klu."""
+    if op.ndim != 2 or op.shape[0] % 2 == 0 or op.shape[1] != n:
+        raise ValueError("%s: op must have shape (2*klu+1, %d), got %r" % (what, n, op.shape))
+    k = (op.shape[0] - 1) // 2
+    _check_n(klu, k, what)
+    return k
+
+
+def _blocks(blocks, orders, what, n):
+    m = orders.shape[0]
+    if orders.ndim != 1 or blocks.ndim != 2 or blocks.shape != (n, 2 * m - 1):
+        raise ValueError("%s: blocks must have shape (%d, 2*m-1) with m = len(orders) = %d, got %r"
+                         % (what, n, m, blocks.shape))
+    return m
+
+
+_PINNED_FROM = 1 << 20   # results of at least this many bytes are returned in page-locked memory
+
+
+def _result_like(a, order="C"):
+    """Uninitialised result array of a's shape.  Large results live in page-locked host memory (from torch's caching
+    host allocator, reused between calls) so that the device-to-host copy runs at the speed of the bus; the array
+    is an ordinary numpy array to the caller (the f2py module returns a fresh numpy-owned array too)."""
+    if a.nbytes >= _PINNED_FROM and a.ndim in (1, 2):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                dt = {np.dtype(np.float64): torch.float64, np.dtype(np.complex128): torch.complex128}[a.dtype]
+                shape = a.shape if order == "C" else a.shape[::-1]
+                out = torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+                return out if order == "C" else out.T
+        except Exception:       # no torch / no pinned memory: pageable result, same values
+            pass
+    return np.empty(a.shape, dtype=a.dtype, order=order)
+
+
 def _check_n(n, inferred, what):
     if n is not None and int(n) != inferred:
         raise ValueError("%s: n = %d does not match the array extent %d" % (what, n, inferred))
@@ -129,8 +174,9 @@ class _Module(object):
             raise TypeError("rgbmv: u is updated in place and must be a contiguous float64 vector")
         x = _real(x)
         _check_n(n, u.shape[0], "rgbmv")
-        _check_n(klu, (op.shape[0] - 1) // 2, "rgbmv")
-        _lib.call("nlsb_rgbmv", _ptr(x), _ptr(u), float(sign), _ptr(op), (op.shape[0] - 1) // 2, u.shape[0])
+        _same_shape("rgbmv", "u", u, x=x)
+        k = _band(op, "rgbmv", u.shape[0], klu)
+        _lib.call("nlsb_rgbmv", _ptr(x), _ptr(u), float(sign), _ptr(op), k, u.shape[0])
 
     @staticmethod
     def rbbmv(x, y, sign, blocks, ms, n, m=None):
@@ -142,6 +188,7 @@ class _Module(object):
         x = _real(x)
         if x.shape != (n * n,) or y.shape != (n * n,):
             raise ValueError("rbbmv: x and y must have n*n entries")
+        _blocks(blocks, ms, "rbbmv", n)
         _lib.call("nlsb_rbbmv", _ptr(x), _ptr(y), float(sign), _ptr(blocks), _ptr(ms), ms.shape[0], n)
 
     def rbbmv_o3(self, x, y, sign, blocks, ms, n):
@@ -157,7 +204,10 @@ class _Module(object):
     @staticmethod
     def revervoir(pumping, coeffs, u_sqr, n=None):
         p, q = _real(pumping), _real(u_sqr)
+        if p.ndim != 1:
+            raise ValueError("revervoir: pumping must be a vector (got shape %r)" % (p.shape,))
         _check_n(n, p.shape[0], "revervoir")
+        _same_shape("revervoir", "pumping", p, u_sqr=q)
         r = np.empty_like(p)
         _lib.call("nlsb_revervoir", _ptr(p), _ptr(_coeffs(coeffs)), _ptr(q), _ptr(r), p.shape[0])
         return r
@@ -166,7 +216,8 @@ class _Module(object):
     def revervoir_2d(pumping, coeffs, u_sqr, n=None):
         p, q = _real(pumping), _real(u_sqr)
         _check_n(n, _square(p, "pumping"), "revervoir_2d")
-        r = np.empty_like(p)
+        _same_shape("revervoir_2d", "pumping", p, u_sqr=q)
+        r = _result_like(p)
         _lib.call("nlsb_revervoir_2d", _ptr(p), _ptr(_coeffs(coeffs)), _ptr(q), _ptr(r), p.shape[0])
         return r
 
@@ -174,10 +225,13 @@ class _Module(object):
     @staticmethod
     def hamiltonian(pumping, coeffs, u, op, klu=None, n=None):
         op, u, p = _real(op, "F"), _cplx(u), _real(pumping)
+        if u.ndim != 1:
+            raise ValueError("hamiltonian: u must be a vector (got shape %r)" % (u.shape,))
         _check_n(n, u.shape[0], "hamiltonian")
+        _same_shape("hamiltonian", "u", u, pumping=p)
+        k = _band(op, "hamiltonian", u.shape[0], klu)
         v = np.empty_like(u)
-        _lib.call("nlsb_hamiltonian", _ptr(p), _ptr(_coeffs(coeffs)), _ptr(u), _ptr(v), _ptr(op),
-                  (op.shape[0] - 1) // 2, u.shape[0])
+        _lib.call("nlsb_hamiltonian", _ptr(p), _ptr(_coeffs(coeffs)), _ptr(u), _ptr(v), _ptr(op), k, u.shape[0])
         return v
 
     @staticmethod
@@ -186,7 +240,9 @@ class _Module(object):
         blocks, u, p = _real(blocks, "F"), _cplx(u, "F"), _real(pumping, "F")
         orders = np.ascontiguousarray(orders, dtype=np.int32)
         _check_n(n, _square(u, "u"), "hamiltonian_2d")
-        v = np.empty(u.shape, dtype=np.complex128, order="F")
+        _same_shape("hamiltonian_2d", "u", u, pumping=p)
+        _check_n(order, _blocks(blocks, orders, "hamiltonian_2d", u.shape[0]), "hamiltonian_2d")
+        v = _result_like(u, "F")
         _lib.call("nlsb_hamiltonian_2d", _ptr(p), _ptr(_coeffs(coeffs)), _ptr(u), _ptr(v), _ptr(blocks),
                   _ptr(orders), orders.shape[0], u.shape[0])
         return v
@@ -195,7 +251,11 @@ class _Module(object):
     @staticmethod
     def runge_kutta(dt, t0, u0, op, iters, pumping, coeffs, n=None, order=None):
         op, u0, p = _real(op, "F"), _cplx(u0), _real(pumping)
+        if u0.ndim != 1:
+            raise ValueError("runge_kutta: u0 must be a vector (got shape %r)" % (u0.shape,))
         _check_n(n, u0.shape[0], "runge_kutta")
+        _same_shape("runge_kutta", "u0", u0, pumping=p)
+        _check_n(order, 2 * _band(op, "runge_kutta", u0.shape[0]) + 1, "runge_kutta")
         u = np.empty_like(u0)
         _lib.call("nlsb_runge_kutta", float(dt), float(t0), _ptr(u0), _ptr(op), u0.shape[0], op.shape[0],
                   int(iters), _ptr(u), _ptr(p), _ptr(_coeffs(coeffs)))
@@ -206,7 +266,9 @@ class _Module(object):
         blocks, u0, p = _real(blocks, "F"), _cplx(u0, "F"), _real(pumping, "F")
         orders = np.ascontiguousarray(orders, dtype=np.int32)
         _check_n(n, _square(u0, "u0"), "runge_kutta_2d")
-        u = np.empty(u0.shape, dtype=np.complex128, order="F")
+        _same_shape("runge_kutta_2d", "u0", u0, pumping=p)
+        _check_n(order, _blocks(blocks, orders, "runge_kutta_2d", u0.shape[0]), "runge_kutta_2d")
+        u = _result_like(u0, "F")
         _lib.call("nlsb_runge_kutta_2d", float(dt), float(t0), _ptr(u0), u0.shape[0], _ptr(blocks), _ptr(orders),
                   orders.shape[0], int(iters), _ptr(u), _ptr(p), _ptr(_coeffs(coeffs)))
         return u
@@ -236,7 +298,7 @@ class _Module(object):
         if p.shape != u0.shape:
             raise ValueError("solve_nls_2d: pumping and u0 must have the same shape")
         _check_n(n, nn, "solve_nls_2d")
-        u = np.empty_like(u0)
+        u = _result_like(u0)
         _lib.call("nlsb_solve_nls_2d", float(dt), float(dx), nn, int(order), int(iters), _ptr(p),
                   _ptr(_coeffs(coeffs)), _ptr(u0), _ptr(u))
         return u
@@ -244,7 +306,10 @@ class _Module(object):
     @staticmethod
     def chemical_potential_1d(dx, pumping, coeffs, u0, n=None):
         u0, p = _cplx(u0), _real(pumping)
+        if u0.ndim != 1:
+            raise ValueError("chemical_potential_1d: u0 must be a vector (got shape %r)" % (u0.shape,))
         _check_n(n, u0.shape[0], "chemical_potential_1d")
+        _same_shape("chemical_potential_1d", "u0", u0, pumping=p)
         mu = np.zeros(1, dtype=np.complex128)
         _lib.call("nlsb_chemical_potential_1d", float(dx), u0.shape[0], _ptr(p), _ptr(_coeffs(coeffs)), _ptr(u0), _ptr(mu))
         return complex(mu[0])
@@ -253,6 +318,7 @@ class _Module(object):
     def chemical_potential_2d(dx, pumping, coeffs, u0, n=None):
         u0, p = _cplx(u0), _real(pumping)
         _check_n(n, _square(u0, "u0"), "chemical_potential_2d")
+        _same_shape("chemical_potential_2d", "u0", u0, pumping=p)
         mu = np.zeros(1, dtype=np.float64)
         _lib.call("nlsb_chemical_potential_2d", float(dx), u0.shape[0], _ptr(p), _ptr(_coeffs(coeffs)), _ptr(u0), _ptr(mu))
         return float(mu[0])

@@ -137,3 +137,46 @@ def test_kernel_choice_and_stream_geometry_for_the_baseline_configs():
     out = [C.c_int() for _ in range(4)]
     assert lib.nlsb_dev_rk4_2d_plan(1, 1072, 8192, 5, *[C.byref(v) for v in out]) == 0
     assert out[2].value * -(-1072 // out[3].value) == 296
+
+
+def test_array_extents_are_checked_before_the_c_abi_sees_pointers():
+    """f2py raises on mismatched extents (check(shape(pumping,0)==n)); the ctypes shim must too -- the C side
+    would otherwise copy n elements out of a shorter host buffer."""
+    c, z8, z88 = np.ones(23), np.ones(8, complex), np.ones((8, 8), complex)
+    orders = np.array([0, 0, 2, 0, 0])
+    cases = [
+        (nls.hamiltonian, (np.ones(5), c, z8, np.ones((5, 8)))),
+        (nls.hamiltonian, (np.ones(8), c, z8, np.ones((5, 7)))),
+        (nls.hamiltonian_2d, (np.ones((8, 7)), c, z88, np.ones((8, 9)), orders)),
+        (nls.hamiltonian_2d, (np.ones((8, 8)), c, z88, np.ones((8, 7)), orders)),
+        (nls.runge_kutta, (1e-3, 0.0, z8, np.ones((5, 8)), 1, np.ones(7), c)),
+        (nls.runge_kutta, (1e-3, 0.0, z8, np.ones((5, 9)), 1, np.ones(8), c)),
+        (nls.runge_kutta_2d, (1e-3, 0.0, z88, np.ones((8, 9)), orders, 1, np.ones((8, 7)), c)),
+        (nls.runge_kutta_2d, (1e-3, 0.0, z88, np.ones((7, 9)), orders, 1, np.ones((8, 8)), c)),
+        (nls.chemical_potential_1d, (0.1, np.ones(9), c, z8)),
+        (nls.chemical_potential_2d, (0.1, np.ones((8, 9)), c, z88)),
+        (nls.revervoir, (np.ones(8), c, np.ones(7))),
+        (nls.revervoir_2d, (np.ones((8, 8)), c, np.ones((8, 7)))),
+        (nls.rgbmv, (np.ones(7), np.ones(8), 1.0, np.ones((5, 8)))),
+        (nls.rgbmv, (np.ones(8), np.ones(8), 1.0, np.ones((5, 9)))),
+        (nls.rbbmv, (np.ones(64), np.ones(64), 1.0, np.ones((7, 9)), orders, 8)),
+        (nls.solve_nls, (1e-3, 0.1, 5, 1, np.ones(9), c, z8)),
+        (nls.solve_nls_2d, (1e-3, 0.1, 5, 1, np.ones((8, 9)), c, z88)),
+    ]
+    for fn, args in cases:
+        with pytest.raises(ValueError):
+            fn(*args)
+
+
+def test_coefficients_outside_the_divide_domain_are_refused():
+    """The fused kernels' divide needs a positive, finite reservoir denominator c13 + c14 |psi|^2 (always true for
+    model.py's coefficient sets: c13 = 1, c14 > 0); other sets are an argument error, not a silent NaN."""
+    good = np.ones(23)
+    for bad_index, bad_value in ((12, 0.0), (12, -1.0), (13, -0.5), (11, np.inf), (2, np.nan)):
+        c = good.copy()
+        c[bad_index] = bad_value
+        with pytest.raises(error) as info:
+            nls.solve_nls(1e-3, 0.1, 5, 1, np.ones(16), c, np.ones(16) * 0.1)
+        assert info.value.status == -1
+        with pytest.raises(error):
+            nls.solve_nls_2d(1e-3, 0.1, 5, 1, np.ones((8, 8)), c, np.ones((8, 8)) * 0.1)

@@ -109,6 +109,34 @@ def test_hamiltonian_device_api():
     assert rel_l2(g.hamiltonian().cpu().numpy()[0], want2) <= 1e-13
 
 
+def test_hamiltonian_of_an_ensemble_larger_than_the_grid_y_limit():
+    """BASELINE config 3 has 65 536 members: one more than gridDim.y allows, so members ride on gridDim.x."""
+    from nls_b200.engine import Ensemble1D
+    n, B = 64, 65536 + 3
+    m = model_1d(n)
+    u = rough_field(n, 9)
+    scale = np.linspace(0.5, 1.5, B)
+    e = Ensemble1D(n, m.dx, m.dt, batch=B, pumping=m.getPumping(), coeffs=m.getCoefficients(), u0=scale[:, None] * u[None, :])
+    got = e.hamiltonian().cpu().numpy()
+    op = O.dp.make_laplacian(n, 5, m.dx)
+    for b in (0, 1, 65534, 65535, 65536, B - 1):
+        want = O.dp.hamiltonian(m.getPumping(), m.getCoefficients(), scale[b] * u, op)
+        assert rel_l2(got[b], want) <= 1e-13, b
+
+
+def test_staged_1d_path_for_systems_larger_than_one_cta_in_a_batch():
+    """n > 2048 takes one launch per stage through global memory (members on gridDim.x there too)."""
+    from nls_b200.engine import Ensemble1D
+    n, B, iters = 2304, 3, 20
+    m = model_1d(n, iters)
+    P = np.array([m.getPumping() * s for s in (0.5, 1.0, 1.5)])
+    e = Ensemble1D(n, m.dx, m.dt, batch=B, pumping=P, coeffs=m.getCoefficients(), u0=0.1)
+    got = e.advance(iters).solution()
+    for b in range(B):
+        want = O.dp.solve_nls(m.dt, m.dx, 5, iters, P[b], m.getCoefficients(), 0.1 * np.ones(n))
+        assert rel_l2(got[b], want) <= 1e-10
+
+
 def _host_diagnostics(m, u, order, dim):
     """The reference's own host-side formulas (model.py mirror) + the oracle's chemical potential."""
     from nls_b200.model import Solution
@@ -303,7 +331,7 @@ def test_advance_until_stops_on_a_device_side_criterion():
     a = Ensemble1D(200, m.dx, m.dt, batch=2, pumping=np.array([m.getPumping(), 1.5 * m.getPumping()]),
                    coeffs=m.getCoefficients(), u0=0.1)
     steps, converged, history = a.advance_until(rel_tol=1e-3, check_every=250, max_iters=20000)
-    assert converged and steps % 250 == 0 and 250 <= steps < 20000 and len(history) == steps // 250 + 1
+    assert converged and steps % 250 == 0 and 500 <= steps < 20000 and len(history) == steps // 250
     last, prev = history[-1], history[-2]
     assert np.max(np.abs(last - prev) / np.abs(last)) <= 1e-3
     b = Ensemble1D(200, m.dx, m.dt, batch=2, pumping=np.array([m.getPumping(), 1.5 * m.getPumping()]),
@@ -311,3 +339,149 @@ def test_advance_until_stops_on_a_device_side_criterion():
     assert np.array_equal(a.solution(), b.solution())
     steps, converged, _ = b.advance_until(rel_tol=0.0, check_every=7, max_iters=20)
     assert steps == 20 and not converged
+
+
+# ---- long / large solves against committed oracle fixtures (tests/golden/make_golden_2d.py) ----------------------
+def _against_fixture(case, path="auto"):
+    """Run the engine on the fixture's inputs and compare with the dp oracle's reduced field: the strided sub-sample,
+    the complex sum and the |psi|^2 sum of EVERY row and column, and the norm -- all to 1e-10 (BASELINE tolerance)."""
+    import importlib.util
+    import os
+    import torch
+    from nls_b200.engine import Grid2D
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_2d", os.path.join(here, "golden", "make_golden_2d.py"))
+    gold = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gold)
+    fix = np.load(os.path.join(here, "golden", "solve2d_%s.npz" % case))
+    P, coeffs, u0, dx, dt, order = gold.inputs(case)
+    grid = Grid2D(u0.shape[0], dx, dt, order=order, pumping=P, coeffs=coeffs, u0=u0)
+    del P, u0
+    psi = grid.advance(int(fix["iters"])).psi[0]
+    s = int(fix["stride"])
+    a2 = psi.real ** 2 + psi.imag ** 2
+    got = dict(sub=psi[::s, ::s], row_sum=psi.sum(dim=1), col_sum=psi.sum(dim=0), row_abs2=a2.sum(dim=1),
+               col_abs2=a2.sum(dim=0))
+    errs = {}
+    for key, value in got.items():
+        want = torch.from_numpy(fix[key]).to(value.device)
+        errs[key] = float(torch.linalg.vector_norm((value - want).reshape(-1)) / torch.linalg.vector_norm(want.reshape(-1)))
+    errs["norm"] = abs(float(torch.sqrt(a2.sum())) - float(fix["norm"])) / float(fix["norm"])
+    return errs
+
+
+def test_c2_full_horizon_against_the_oracle():
+    """examples/solve2d.py at 512^2 for its FULL 5000 steps (BASELINE config 2), engine vs dp oracle <= 1e-10."""
+    errs = _against_fixture("c2_full")
+    assert max(errs.values()) <= 1e-10, errs
+
+
+def test_c4_size_three_steps_against_the_oracle():
+    """8192^2 (BASELINE config 4 size, strip-marching kernel), rough initial field, 3 steps, vs dp oracle <= 1e-10."""
+    errs = _against_fixture("c4_3steps")
+    assert max(errs.values()) <= 1e-10, errs
+
+
+def test_c5_member_200_steps_against_the_oracle():
+    """One member of BASELINE config 5 (1024^2, pump radius 16.9), rough initial field, 200 steps, <= 1e-10."""
+    errs = _against_fixture("c5_member")
+    assert max(errs.values()) <= 1e-10, errs
+
+
+def test_fast_divide_equals_the_ieee_divide_on_its_domain():
+    """div_fast (csrc/device_math.cuh: MUFU.RCP64H seed + Newton step + residual correction) is on every hot kernel;
+    here 2^24 operand pairs from the reservoir's domain (denominator = c13 + c14 |psi|^2 >= c13, numerator c12 P of
+    either sign and any magnitude) plus structured hard cases go through it and through __ddiv_rn on the device."""
+    import ctypes as C
+    import torch
+    from nls_b200 import _lib
+    n = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(7)
+    b = 1.0 + torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * 10.0 ** (torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * 8 - 4)
+    a = (torch.rand(n, generator=g, device="cuda", dtype=torch.float64) - 0.3) * 10.0 ** (torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * 12 - 8)
+    # structured: denominators one ulp around powers of two and around 1, numerators that make ties likely
+    k = torch.arange(1 << 16, device="cuda", dtype=torch.float64)
+    b[: 1 << 16] = 1.0 + k * 2.0 ** -52
+    b[1 << 16: 2 << 16] = 2.0 - (k + 1) * 2.0 ** -52
+    b[2 << 16: 3 << 16] = (1.0 + k * 2.0 ** -30) * 2.0 ** 40
+    a[: 3 << 16] = torch.where(k.repeat(3) % 2 == 0, 1.0 + k.repeat(3) * 2.0 ** -51, 3.0 - k.repeat(3) * 2.0 ** -50)
+    fast, exact = torch.empty_like(a), torch.empty_like(a)
+    _lib.call("nlsb_dev_divide_check", C.c_size_t(n), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+              C.c_void_p(fast.data_ptr()), C.c_void_p(exact.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert bool(torch.equal(exact, a / b))                       # torch's divide is the IEEE one as well
+    ulps = (fast.view(torch.int64) - exact.view(torch.int64)).abs()
+    mismatches = int((ulps != 0).sum())
+    assert mismatches == 0, (mismatches, int(ulps.max()))
+
+
+# ---- diagnostics fused into the last step's launch (SURVEY 8f row 1) ---------------------------------------------
+def _diag_close(got, want, tol=1e-12):
+    for key in ("chemical_potential", "damping_integral", "particles", "max_density", "max_reservoir"):
+        scale = np.maximum(np.abs(want[key]), np.abs(want["particles"]) * 1e-3 if key == "damping_integral" else 1e-300)
+        assert np.all(np.abs(got[key] - want[key]) <= tol * scale), (key, got[key], want[key])
+
+
+def test_fused_diagnostics_1d_equal_the_standalone_pass():
+    from nls_b200.engine import Ensemble1D
+    m = model_1d(400)
+    P = np.array([m.getPumping() * s for s in (0.5, 1.0, 2.0)])
+    for order in (3, 5, 7):
+        mk = lambda: Ensemble1D(400, m.dx, m.dt, order=order, batch=3, pumping=P, coeffs=m.getCoefficients(), u0=0.1)
+        a, b = mk(), mk()
+        want = a.advance(36).diagnostics()          # state after 36 steps = the state entering step 37
+        a.advance(1)
+        got = b.advance(37, diagnostics=True)
+        assert got["step"] == 36
+        _diag_close(got, want)
+        assert np.array_equal(a.solution(), b.solution())            # the fused reduction never changes the field
+        again = mk().advance(37, diagnostics=True)
+        assert all(np.array_equal(again[k], got[k]) for k in want)   # fixed summation order: reproducible bits
+
+
+@pytest.mark.parametrize("order,n,batch", [(5, 1024, 1), (5, 1024, 2), (3, 1024, 1), (7, 1056, 1), (5, 96, 2), (5, 1025, 1)])
+def test_fused_diagnostics_2d_equal_the_standalone_pass(order, n, batch):
+    """1024-wide grids take the strip-marching kernel (reduction inside the last launch); 96 / 513 the tile kernel
+    (stand-alone pass before the last step): one API, one meaning."""
+    from nls_b200.engine import Grid2D
+    from nls_b200.model import dimensionless_coefficients, DEFAULT_ORIGINAL_PARAMS
+    m = model_2d(n, radius=min(10.0, n * 0.1 / 4))
+    u0 = 0.1 + 0.05 * rough_field((n, n), n)
+    c = np.array([dimensionless_coefficients(dict(DEFAULT_ORIGINAL_PARAMS, gamma_R=g)) for g in (0.242057488654, 0.5)][:batch])
+    P = np.array([m.getPumping() * s for s in (1.0, 0.7)][:batch])
+    mk = lambda: Grid2D(n, m.dx, m.dt, order=order, batch=batch, pumping=P, coeffs=c, u0=u0)
+    a, b = mk(), mk()
+    want = a.advance(4).diagnostics()
+    a.advance(1)
+    got = b.advance(5, diagnostics=True)
+    assert got["step"] == 4
+    _diag_close(got, want)
+    assert np.array_equal(a.solution(), b.solution())
+    again = mk().advance(5, diagnostics=True)
+    assert all(np.array_equal(again[k], got[k]) for k in want)
+
+
+def test_fused_diagnostics_cost_nothing_extra_on_the_large_grid():
+    """A 4096^2 chunk of 20 steps with the reduction riding in its last launch is <= 5 % slower than the plain chunk."""
+    import torch
+    from nls_b200.engine import Grid2D
+    n = 4096
+    m = model_2d(n, radius=100.0)
+    g = Grid2D(n, m.dx, m.dt, order=5, pumping=m.getPumping(), coeffs=m.getCoefficients(), u0=0.1)
+
+    def timed(fn):
+        best = 1e30
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    g.advance(20)
+    g.advance(20, diagnostics=True)
+    plain = timed(lambda: g.advance(20))
+    fused = timed(lambda: g.advance(20, diagnostics=True))
+    assert fused <= 1.05 * plain, (plain, fused)

@@ -58,7 +58,7 @@ def _run_peer(n, iters, world, order, halo_steps, graphs):
     m = model_2d(n, iters, order=order, radius=min(10.0, n * 0.1 / 4))
     u0 = 0.1 + 0.05 * rough_field((n, n), n)
     slabs = [SlabGrid2D(n, m.dx, m.dt, order, m.getPumping(), m.getCoefficients(), u0, rank=r, world=world,
-                        stepper=_cuda_stepper_interleaved, halo_steps=halo_steps, exchange="local")
+                        stepper=_cuda_stepper_interleaved, halo_steps=halo_steps, exchange="local", device="cuda")
              for r in range(world)]
     link_local_peers(slabs)
     for g in slabs:

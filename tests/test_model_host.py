@@ -138,5 +138,23 @@ def test_mat_store_restore_roundtrip(tmp_path, monkeypatch):
     assert more.getSolution().shape == (32,)
 
 
+def test_checkpoints_written_by_the_reference_restore(tmp_path, monkeypatch):
+    """The reference stores str(type(model)) = "<class 'nls.model.Model2D'>" (ref model.py:265); same field layout."""
+    from scipy.io import loadmat, savemat
+    monkeypatch.setattr(S, "nls", _OracleNative())
+    m = M.Problem().model(model="2d", num_nodes=12, num_iters=2, order=3,
+                          pumping=GaussianRingPumping2D(power=2.0, radius=0.4, variation=0.2))
+    path = str(tmp_path / "own.mat")
+    m.solve().store(path, label="t", desc="d")
+    mat = {k: v for k, v in loadmat(path).items() if not k.startswith("__")}
+    for ref_name, cls in (("<class 'nls.model.Model2D'>", M.Model2D), ("nls.model.Model2D", M.Model2D)):
+        mat["model"] = ref_name
+        ref_path = str(tmp_path / "ref.mat")
+        savemat(ref_path, mat)
+        again = M.Problem().model(filename=ref_path)
+        assert isinstance(again, cls) and again.num_nodes == 12
+        assert np.array_equal(again.getPumping(), m.getPumping())
+
+
 def test_version():
     assert nls_b200.version() == (0, 2, 0)
