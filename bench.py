@@ -118,21 +118,58 @@ def points(w):
 
 # ---- clocks -----------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: an in-process NVML thread
+    (every 20 ms; the timed regions of the multi-GPU runs last a fraction of a second), or -- without pynvml -- the
+    recipe's `nvidia-smi ... -lms` subprocess."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    NVML_BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, period_s=0.02):
+        self.rows, self.proc, self.index, self.period = [], None, index, period_s
+        self.thread, self.stop, self.source = None, threading.Event(), None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+
+            def pump():
+                while not self.stop.is_set():
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                        watts = pynvml.nvmlDeviceGetPowerUsage(handle) / 1e3
+                        bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                        self.rows.append([str(mhz), str(smax), str(watts)] +
+                                         ["Active" if bits & self.NVML_BITS[n] else "Not Active" for n in self.NAMES])
+                    except Exception:
+                        pass
+                    self.stop.wait(self.period)
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            self.source = "nvml thread, %d ms" % int(1e3 * self.period)
+            return self
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.source = "nvidia-smi -lms 50"
         except OSError:
             self.proc = None
         return self
@@ -142,17 +179,19 @@ class ClockSampler(object):
             self.rows.append([f.strip() for f in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        if self.thread:
             self.thread.join(timeout=2)
 
     def summary(self):
         sm, smax, watts, reasons = [], [], [], set()
-        for r in self.rows:
+        for r in list(self.rows):
             try:
                 sm.append(float(r[0]))
                 smax.append(float(r[1]))
@@ -163,9 +202,9 @@ class ClockSampler(object):
                 if val == "Active":
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm), "sm_mhz_min": float(min(sm)), "power_w_max": float(max(watts))}
+                "samples": len(sm), "sm_mhz_min": float(min(sm)), "power_w_max": float(max(watts)), "source": self.source}
 
 
 def measured_hbm_peak():
@@ -483,7 +522,7 @@ def run_engine(args):
     set_2d_path(args.path)
     env = Env(args)
     name = args.workload
-    rec = measure(env, args, name, args.steps, args.warmup, iters=args.iters, with_e2e=True)
+    rec = measure(env, args, name, args.steps, args.warmup, iters=args.iters, warmup_iters=args.warmup_iters, with_e2e=True)
     line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": rec["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": rec["config"],
@@ -529,6 +568,8 @@ def main():
     ap.add_argument("--also", default="default", help="comma list of other workloads measured as sub-records, 'none', or "
                     "'default' (c2,c3,c5 on one GPU; c3,c5 sharded on several)")
     ap.add_argument("--iters", type=int, default=None, help="RK steps per bench step (default: the workload's)")
+    ap.add_argument("--warmup-iters", type=int, default=None, help="RK steps per WARM-UP step (default: as the timed steps; "
+                    "set it low for full-horizon runs such as --workload c5 --iters 100000 --steps 1)")
     ap.add_argument("--batch", type=int, default=None, help="override the ensemble size")
     ap.add_argument("--grid-n", dest="n", type=int, default=None, help="override the grid size (profiling only)")
     ap.add_argument("--order", type=int, default=None, help="override the stencil order (profiling only)")

@@ -185,7 +185,9 @@ static std::atomic<int> g_path_2d{0};
 
 static bool stream_preferred(int order, int batch, int out_rows, int cols)
 {
-    return (cols & 1) == 0 && (long long)batch * out_rows * cols >= (1ll << 20);
+    (void)order;
+    (void)cols;
+    return (long long)batch * out_rows * cols >= (1ll << 20);
 }
 
 static int launch_interleaved_step(int order, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream)
@@ -221,9 +223,10 @@ struct DiagRequest {
 // Fused path: one launch per RK step, psi ping-pongs between `psi` and the first plane of `work`.
 void enqueue_fused_steps_2d(int batch, int rows, int cols, int order, double dt, const CrossWeights &w,
                             const double *pumping, const double *coeffs, double2 *psi, double2 *work, int first_step,
-                            int nsteps, cudaStream_t stream, int *rc, const DiagRequest *diag_on_last = nullptr)
+                            int nsteps, cudaStream_t stream, int *rc, const DiagRequest *diag_on_last = nullptr, int p_pitch = 0)
 {
     Fused2DStep s{batch, rows, cols, 0, rows, 0, rows, nullptr, nullptr, pumping, coeffs, dt, g_uniform_coeffs};
+    s.p_pitch = p_pitch;
     for (int i = 0; i < nsteps; ++i) {
         const bool even = ((first_step + i) & 1) == 0;
         s.in = even ? psi : work;
@@ -266,6 +269,21 @@ int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, do
     const int chunk = 32;   // even: a replayed chunk starts and ends in `psi`
     int done = 0;
     const int replayable = diag ? iters - 1 : iters;      // the diagnostics-carrying last step is launched directly
+    // The strip-marching kernel fetches the pumping rows with TMA (16-byte row stride and base): a grid with an odd
+    // number of columns gets a copy with an even pitch, made once per time loop in the unused part of the work space
+    // (the loop ping-pongs between psi and the first psi-sized plane of `work`); 8 + 8 bytes per node, once.
+    int p_pitch = 0;
+    {
+        const int path = g_path_2d.load();
+        const bool marching = path == 8 || (path == 0 && stream_preferred(order, batch, rows, cols));
+        if (marching && iters > 0 && ((cols & 1) || (reinterpret_cast<uintptr_t>(pumping) & 15) != 0)) {
+            p_pitch = (cols + 1) & ~1;
+            double *padded = reinterpret_cast<double *>(work + (size_t)batch * rows * cols);
+            NLSB_CUDA(cudaMemcpy2DAsync(padded, sizeof(double) * p_pitch, pumping, sizeof(double) * cols, sizeof(double) * cols,
+                                        (size_t)batch * rows, cudaMemcpyDeviceToDevice, stream));
+            pumping = padded;
+        }
+    }
     if (cap == cudaStreamCaptureStatusNone && replayable >= 2 * chunk) {
         LoopKey key;
         std::memset(&key, 0, sizeof(key));
@@ -289,7 +307,7 @@ int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, do
             cudaStream_t rec;
             NLSB_TRY(internal_stream(&rec));
             NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
-            enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, &rc);
+            enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, &rc, nullptr, p_pitch);
             cudaError_t e = cudaStreamEndCapture(rec, &graph);
             count_launches(0ull - (unsigned long long)chunk);
             if (rc) {
@@ -312,7 +330,7 @@ int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, do
             count_launches((unsigned long long)chunk);
         }
     }
-    enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, done, iters - done, stream, &rc, diag);
+    enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, done, iters - done, stream, &rc, diag, p_pitch);
     if (rc) return rc;
     if (iters & 1)
         NLSB_CUDA(cudaMemcpyAsync(psi, work, sizeof(double2) * (size_t)batch * rows * cols, cudaMemcpyDeviceToDevice, stream));
@@ -1028,9 +1046,7 @@ int nlsb_dev_rk4_2d_diag(int batch, int rows, int cols, int order, int iters, do
     double2 *p = reinterpret_cast<double2 *>(psi);
     double2 *work = static_cast<double2 *>(workspace);
     const int path = g_path_2d.load();
-    Fused2DStep probe{batch, rows, cols, 0, rows, 0, rows, p, work, pumping, coeffs, dt, g_uniform_coeffs};
-    const bool fused = (path == 8 || (path == 0 && stream_preferred(order, batch, rows, cols))) && stream_2d_takes(probe) &&
-                       batch <= 32767 * 2;
+    const bool fused = (path == 8 || (path == 0 && stream_preferred(order, batch, rows, cols))) && batch <= 65535;
     if (fused) {
         // the reduction rides in the first stage of the last step's launch; a tiny second launch sums the CTAs' partials
         const DiagRequest req{diag_scratch, dx * dx};
@@ -1127,11 +1143,7 @@ int nlsb_dev_rk4_2d_plan(int batch, int rows, int cols, int order, int *kernel, 
     const int path = g_path_2d.load();
     *strips = *chunk_rows = 0;
     if (path == 8 || (path == 0 && stream_preferred(order, batch, rows, cols))) {
-        if (cols & 1) {                       // the streaming launcher hands odd widths to the 32x32 tile kernel
-            *kernel = 0; *threads = 256;
-            return 0;
-        }
-        *kernel = 2;
+        *kernel = 2;                          // odd widths too: the time loop hands over a pitched copy of the pumping
         return stream_2d_plan(order, batch, rows, cols, threads, strips, chunk_rows);
     }
     int sms = 148, dev = 0;

@@ -55,6 +55,10 @@ struct Fused2DStep {
     // (`in`) into [batch][stream_2d_diag_parts] partial sums (diag_acc.cuh), area element diag_area
     void *diag_partial = nullptr;
     double diag_area = 0.0;
+    // strip-marching kernel only: elements between rows of `pumping` (0 = cols).  The pumping rows are fetched by
+    // TMA, whose row stride must be a multiple of 16 bytes: grids with an odd number of columns hand over a copy of
+    // the pumping with an even pitch (api.cu makes it once per time loop)
+    int p_pitch = 0;
 };
 // variant 0: 32x32 tiles, two CTAs per SM; variant 1: 32x64 tiles, one CTA of 512 threads per SM
 int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);

@@ -194,8 +194,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // complex = true: interleaved complex128 [batch][rows][cols] as a (2, cols, rows, batch) tensor of doubles;
-// complex = false: float64 [batch][rows][cols] as (cols, rows, batch) (cols must be even: 16-byte row stride)
-int encode_field_map(TensorMap *out, const void *base, bool complex, int batch, int rows, int cols, int box_cols, int box_rows)
+// complex = false: float64 [batch][rows][pitch] as (cols, rows, batch) (pitch must be even: 16-byte row stride)
+int encode_field_map(TensorMap *out, const void *base, bool complex, int batch, int rows, int cols, int pitch, int box_cols,
+                     int box_rows)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -219,7 +220,7 @@ int encode_field_map(TensorMap *out, const void *base, bool complex, int batch, 
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-        const cuuint64_t strides[2] = {(cuuint64_t)cols * sizeof(double), (cuuint64_t)cols * rows * sizeof(double)};
+        const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(double), (cuuint64_t)pitch * rows * sizeof(double)};
         const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
         r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -235,11 +236,11 @@ int encode_field_map(TensorMap *out, const void *base, bool complex, int batch, 
 struct MapKey {
     const void *base;
     bool complex;
-    int batch, rows, cols, box_cols, box_rows;
+    int batch, rows, cols, pitch, box_cols, box_rows;
     bool operator==(const MapKey &o) const
     {
-        return base == o.base && complex == o.complex && batch == o.batch && rows == o.rows && cols == o.cols && box_cols == o.box_cols &&
-               box_rows == o.box_rows;
+        return base == o.base && complex == o.complex && batch == o.batch && rows == o.rows && cols == o.cols && pitch == o.pitch &&
+               box_cols == o.box_cols && box_rows == o.box_rows;
     }
 };
 
@@ -254,7 +255,7 @@ int cached_map(const MapKey &key, TensorMap *out)
             *out = maps[i];
             return 0;
         }
-    int rc = encode_field_map(out, key.base, key.complex, key.batch, key.rows, key.cols, key.box_cols, key.box_rows);
+    int rc = encode_field_map(out, key.base, key.complex, key.batch, key.rows, key.cols, key.pitch, key.box_cols, key.box_rows);
     if (rc) return rc;
     keys[next] = key;
     maps[next] = *out;
@@ -361,9 +362,9 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
     StreamWeights<C::K> wa;
     for (int i = 0; i < C::NW; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
     TensorMap map, map_p;
-    rc = cached_map(MapKey{s.in, true, s.batch, s.rows, s.cols, C::T, C::RB}, &map);
+    rc = cached_map(MapKey{s.in, true, s.batch, s.rows, s.cols, s.cols, C::T, C::RB}, &map);
     if (rc) return rc;
-    rc = cached_map(MapKey{s.pumping, false, s.batch, s.rows, s.cols, C::T, C::RB}, &map_p);
+    rc = cached_map(MapKey{s.pumping, false, s.batch, s.rows, s.cols, s.p_pitch ? s.p_pitch : s.cols, C::T, C::RB}, &map_p);
     if (rc) return rc;
     const int chunks = (out_rows + a.chunk_rows - 1) / a.chunk_rows;
     const dim3 grid((unsigned)(a.strips * chunks), (unsigned)s.batch);
@@ -461,7 +462,8 @@ int stream_2d_plan(int order, int batch, int out_rows, int cols, int *threads, i
 // Whether launch_rk4_step_stream_2d runs the strip-marching kernel for this step (else it hands over to the tile kernel).
 bool stream_2d_takes(const Fused2DStep &s)
 {
-    return (s.cols & 1) == 0 && (reinterpret_cast<uintptr_t>(s.pumping) & 15) == 0;
+    const int pitch = s.p_pitch ? s.p_pitch : s.cols;
+    return (pitch & 1) == 0 && (reinterpret_cast<uintptr_t>(s.pumping) & 15) == 0;
 }
 
 // CTAs per member of the launch = partial sums per member a diagnostics-carrying step writes.
@@ -476,8 +478,12 @@ int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeight
 {
     if (s.batch > 65535) return fail(NLSB_ESIZE, "batch = %d exceeds the grid y-limit 65535", s.batch);
     if ((reinterpret_cast<uintptr_t>(s.in) & 15) != 0) return fail(NLSB_EINVAL, "psi must be 16-byte aligned");
-    // the pumping's tensor map needs a 16-byte row stride and base: other grids take the tile kernel (same bits)
-    if ((s.cols & 1) || (reinterpret_cast<uintptr_t>(s.pumping) & 15) != 0) return launch_rk4_step_fused_2d(order, 0, s, w, stream);
+    // the pumping's tensor map needs a 16-byte row stride and base: callers that cannot provide them (one-off slab
+    // steps on grids with an odd number of columns) get the tile kernel -- same bits
+    if (!stream_2d_takes(s)) {
+        if (s.p_pitch && s.p_pitch != s.cols) return fail(NLSB_EINVAL, "a pitched pumping copy must have an even pitch and a 16-byte aligned base");
+        return launch_rk4_step_fused_2d(order, 0, s, w, stream);
+    }
     switch (order) {
     case 3: return launch_stream_order<1>(s, w, stream);
     case 5: return launch_stream_order<2>(s, w, stream);

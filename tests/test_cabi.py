@@ -120,7 +120,7 @@ def test_kernel_choice_and_stream_geometry_for_the_baseline_configs():
 
     assert plan(1, 512)[:2] == [1, 512]            # C2: one wave of 32x64 tiles
     assert plan(1, 400)[0] in (0, 1) and plan(1, 256)[:2] == [0, 256] and plan(1, 768)[:2] == [0, 256]
-    assert plan(1, 513)[0] in (0, 1)               # odd widths never reach the strip-marching kernel
+    assert plan(1, 513)[0] in (0, 1) and plan(1, 1025)[0] == 2     # odd widths stream too (pitched pumping copy)
     for batch, n, order in ((1, 8192, 5), (256, 1024, 5), (1, 2048, 5), (1, 4096, 3), (1, 4096, 7), (8, 1024, 5)):
         kernel, threads, strips, chunk = plan(batch, n, order)
         k = (order - 1) // 2
