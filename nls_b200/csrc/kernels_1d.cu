@@ -17,6 +17,8 @@
 #include "diag_acc.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace nlsb {
 
 namespace {
@@ -106,8 +108,10 @@ rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, co
                     lr = fma(a, w[p + t].x, lr);
                     li = fma(a, w[p + t].y, li);
                 }
-                double2 k = rhs_point(c, cp[p], w[K + p], lr, li);
-                if (!live[p]) k = make_double2(0.0, 0.0);
+                // Nodes beyond the end of the system need no mask: their psi, c12*P and operator rows are zero, so their k is
+                // exactly zero (rhs_point of zeros) and they stay zero -- the right edge sees the truncated band matrix.
+                // (On B200 every non-FP64 instruction costs this FP64-bound loop an issue cycle: tools/micro/fp64_issue.cu.)
+                const double2 k = rhs_point(c, cp[p], w[K + p], lr, li);
                 if (DIAG && s == 0 && it == iters - 1 && live[p]) {
                     const int i = i0 + p;
                     diag_accumulate(dacc, c, cp[p], w[K + p], k, ((double)(i + 1) - 1.0) * dx,      // nls.f90:940-947
@@ -265,8 +269,12 @@ template <int M>
 int launch_resident_m(int batch, int n, int iters, double dt, const double *taps, const double *pumping,
                       const double *coeffs, double2 *psi, double dx, double *out8, cudaStream_t stream)
 {
+    static const int force_one = [] {
+        const char *e = std::getenv("NLSB_1D_ONE_CTA");        // tuning knob: 1 = always the one-CTA-per-SM flavour
+        return e ? std::atoi(e) : 0;
+    }();
     if (n <= 4 * kResidentThreads) {
-        if (M <= 5 && batch >= 2 * 148)   // enough members for two CTAs on every SM
+        if (M <= 5 && batch >= 2 * 148 && !force_one)   // enough members for two CTAs on every SM
             return launch_resident<M, 4, true, (M <= 5) ? 2 : 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
         return launch_resident<M, 4, true, 1>(batch, n, iters, dt, taps, pumping, coeffs, psi, dx, out8, stream);
     }

@@ -18,6 +18,7 @@
 
 #include <cuda.h>
 #include <atomic>
+#include <type_traits>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -154,7 +155,12 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
     // U = 2 RB: the batch boundaries fall on fixed phases of the unrolled body
     const double2 *rh = ring + tid, *ro = ring + U * C::T + tid;
     const double *ph_ = pring + tid, *po_ = pring + U * C::T + tid;
-    for (int itb = 0; itb < g.niter; itb += U) {
+    // One unrolled block of U iterations, with or without the domain masks (see march_iter): a block needs them when
+    // the strip touches the left / right edge of the domain (some frame column within 3K of the strip lies outside)
+    // or when one of the rows j - 3K .. j of its iterations lies outside -- the first / last blocks of the chunks at
+    // the top and bottom of the domain.  Both bodies are compiled; the choice is uniform over the CTA.
+    auto block = [&](auto masked_tag, int itb) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
         for (int ph = 0; ph < U; ++ph) {
             const int it = itb + ph;
@@ -162,7 +168,7 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
                 const int b = (it + 2 * K) / RB;
                 mbar_wait(bar0 + 8 * (b % NB), (b / NB) & 1);
             }
-            march_iter<C, DIAG>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_, &dacc, a.area);
+            march_iter<C, DIAG, MASKED>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_, &dacc, a.area);
             if ((ph + 1) % PERIOD == 0) {
                 __syncthreads();
                 // thread 0 re-requests the batches whose last reader was one of the iterations this barrier closes:
@@ -177,6 +183,16 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
                 }
             }
         }
+    };
+    const int used_c0 = g.c0 - C::SKEW, used_c1 = g.c0 + C::W + C::SKEW;      // columns whose stage values are used
+    const bool edge_strip = used_c0 < 0 || used_c1 > a.cols;
+    const int row_lo = L.dlo, row_hi = L.dlo + L.dspan;
+    for (int itb = 0; itb < g.niter; itb += U) {
+        const int j0 = g.jstart + itb;                                             // stage-1 row of the block's first iteration
+        if (edge_strip || j0 - C::SKEW < row_lo || j0 + U > row_hi)
+            block(std::true_type{}, itb);
+        else
+            block(std::false_type{}, itb);
         const double2 *t = rh; rh = ro; ro = t;
         const double *tp = ph_; ph_ = po_; po_ = tp;
     }

@@ -215,7 +215,14 @@ NLSB_HD const E *ring_row(const E *rh, const E *ro, int srel)
 // DIAG: stage 1 holds k1 = H(psi) of the state ENTERING the step, so the scalar diagnostics of that state (chemical
 // potential sums, damping integral, particle number, peak density / reservoir: diag_acc.cuh) are accumulated there
 // for the nodes this CTA produces -- no extra pass over the field, no stencil evaluated twice.
-template <class C, bool DIAG = false>
+//
+// MASKED = false: the caller guarantees that every node this iteration evaluates for later use lies inside the
+// domain (rows j - 3K .. j of an interior block of iterations, all frame columns of an interior strip), so the
+// "zero outside the domain" selects vanish: per iteration 12 FSEL, the register moves that feed their results to the
+// stage-ring stores and the row comparisons -- about a third of the loop's non-FP64 instructions.  On B200 an FP64
+// instruction holds the scheduler's issue port for two cycles and EVERY other instruction for one
+// (tools/micro/fp64_issue.cu), so those instructions are paid for in FP64 throughput.
+template <class C, bool DIAG = false, bool MASKED = true>
 NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const RhsCoeffs &c, const double (&wx)[C::NW],
                         const double (&wy)[C::NW], int it, int ph, const double2 *rh, const double2 *ro, const double *ph_,
                         const double *po_, DiagAcc *diag = nullptr, double area = 0.0)
@@ -242,9 +249,9 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
             x4[tp + K] = r4[tp];
         }
     }
-    const bool in1 = L.col_in && row_in_domain(L, j);
-    const bool in2 = L.col_in && row_in_domain(L, j - K);
-    const bool in3 = L.col_in && row_in_domain(L, j - 2 * K);
+    const bool in1 = !MASKED || (L.col_in && row_in_domain(L, j));
+    const bool in2 = !MASKED || (L.col_in && row_in_domain(L, j - K));
+    const bool in3 = !MASKED || (L.col_in && row_in_domain(L, j - 2 * K));
 
     // ---- stage 1, row j -------------------------------------------------------------------------------
     {
@@ -256,7 +263,7 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         cross_stencil<C, U>(s.psi, ci, x1, wx, wy, lr, li);
         const double2 k = rhs_point(c, s.cp[ci], u, lr, li);
         if (DIAG) {
-            if (L.col_owned && (unsigned)(j - g.r0) < (unsigned)(g.r1 - g.r0) && row_in_domain(L, j))
+            if (L.col_owned && (unsigned)(j - g.r0) < (unsigned)(g.r1 - g.r0) && (!MASKED || row_in_domain(L, j)))
                 diag_accumulate(*diag, c, s.cp[ci], u, k, 1.0, area);
         }
         double2 y;
@@ -310,7 +317,7 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         double2 v;
         v.x = fma(s.acc[cu].x + k.x, L.dt6, s.psi[cu].x);
         v.y = fma(s.acc[cu].y + k.y, L.dt6, s.psi[cu].y);
-        store_if(s.onext, v, L.col_owned && (unsigned)(r - g.r0) < (unsigned)(g.r1 - g.r0) && row_in_domain(L, r));
+        store_if(s.onext, v, L.col_owned && (unsigned)(r - g.r0) < (unsigned)(g.r1 - g.r0) && (!MASKED || row_in_domain(L, r)));
         s.onext += L.pitch;
     }
 }

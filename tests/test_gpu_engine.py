@@ -465,7 +465,8 @@ def test_fused_diagnostics_2d_equal_the_standalone_pass(order, n, batch):
 
 
 def test_fused_diagnostics_cost_nothing_extra_on_the_large_grid():
-    """A 4096^2 chunk of 20 steps with the reduction riding in its last launch is <= 5 % slower than the plain chunk."""
+    """A 4096^2 chunk of 50 steps with the reduction riding in its last launch (and its 8 doubles read back) is <= 5 %
+    slower than the plain chunk -- the stand-alone pass alone costs 0.7 RK steps on such a grid."""
     import torch
     from nls_b200.engine import Grid2D
     n = 4096
@@ -483,8 +484,8 @@ def test_fused_diagnostics_cost_nothing_extra_on_the_large_grid():
             best = min(best, a.elapsed_time(b))
         return best
 
-    g.advance(20)
-    g.advance(20, diagnostics=True)
-    plain = timed(lambda: g.advance(20))
-    fused = timed(lambda: g.advance(20, diagnostics=True))
+    g.advance(50)
+    g.advance(50, diagnostics=True)
+    plain = timed(lambda: (g.advance(50), torch.cuda.synchronize()))
+    fused = timed(lambda: g.advance(50, diagnostics=True))
     assert fused <= 1.05 * plain, (plain, fused)
