@@ -287,6 +287,19 @@ int nlsb_peer_enable_access(int peer_device);
 int nlsb_dev_halo_exchange(const double *src_up, double *dst_up, const double *src_down, double *dst_down,
                            size_t complex_count, void *state, void *flags_mine, void *flags_up, void *flags_down,
                            double timeout_seconds, nlsb_stream_t stream);
+/* One RK4 step of a slab AND its halo exchange in ONE launch (strip-marching kernel): as nlsb_dev_rk4_step_2d_slab,
+ * and the `halo_rows` new rows starting at local row up_row0 (dn_row0) are also stored, from the kernel's own store
+ * stage, into the halo rows of the rank above (below) beginning at up_dst (dn_dst) -- peer-mapped pointers into the
+ * neighbour's psi_out buffer.  The launch publishes READY at its start, the CTAs that write into a neighbour wait for
+ * that neighbour's READY, the last CTA publishes DATA and waits for the neighbours' DATA (protocol and blocks as for
+ * nlsb_dev_halo_exchange, with which it shares them).  Fails with NLSB_EINVAL when the launch would not take the
+ * strip-marching kernel (small slabs, odd column counts): use the step + nlsb_dev_halo_exchange then. */
+int nlsb_dev_rk4_step_2d_slab_exchange(int rows_alloc, int cols, int order, double dt, const double *wx, const double *wy,
+                                       int global_row0, int global_rows, int out_row0, int out_row1,
+                                       const double *pumping, const double *coeffs_host, const double *psi_in,
+                                       double *psi_out, int halo_rows, int up_row0, double *up_dst, int dn_row0,
+                                       double *dn_dst, void *state, void *flags_mine, void *flags_up, void *flags_down,
+                                       double timeout_seconds, nlsb_stream_t stream);
 /* Synchronous read-back of a state block: exchanges completed and waits that timed out. */
 int nlsb_dev_halo_status(const void *state, unsigned long long *epoch, unsigned long long *timeouts);
 /* Adds to the count reported by nlsb_kernel_launches(): kernels replayed from a CUDA graph the CALLER captured

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnls_b200.so")
 
 SOURCES = ["api.cu", "kernels_1d.cu", "kernels_2d.cu", "fused_2d.cu", "stream_2d.cu", "resident_2d.cu", "reduce.cu", "diagnostics.cu", "pumping_gen.cu", "peer.cu", "operators.cpp"]
-HEADERS = ["internal.h", "kernels.h", "device_math.cuh", "diag_acc.cuh", "stream_2d_core.cuh", "resident_2d_core.cuh", os.path.join("..", "..", "include", "nls_b200.h")]
+HEADERS = ["internal.h", "kernels.h", "device_math.cuh", "diag_acc.cuh", "peer_flags.cuh", "stream_2d_core.cuh", "resident_2d_core.cuh", os.path.join("..", "..", "include", "nls_b200.h")]
 
 COMPILE_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",

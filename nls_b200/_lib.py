@@ -78,6 +78,8 @@ PROTOTYPES = {
     "nlsb_peer_close": (_I, [_P]),
     "nlsb_peer_enable_access": (_I, [_I]),
     "nlsb_dev_halo_exchange": (_I, [_P, _P, _P, _P, _Z, _P, _P, _P, _P, _F, _P]),
+    "nlsb_dev_rk4_step_2d_slab_exchange": (_I, [_I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _I, _P,
+                                                _P, _P, _P, _P, _F, _P]),
     "nlsb_dev_halo_status": (_I, [_P, _P, _P]),
     "nlsb_add_kernel_launches": (None, [C.c_ulonglong]),
     "nlsb_dev_diagnostics_scratch": (_Z, [_I]),

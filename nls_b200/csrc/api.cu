@@ -1082,6 +1082,49 @@ int nlsb_dev_rk4_step_2d_slab(int rows_alloc, int cols, int order, double dt, co
     return 0;
 }
 
+int nlsb_dev_rk4_step_2d_slab_exchange(int rows_alloc, int cols, int order, double dt, const double *wx, const double *wy,
+                                       int global_row0, int global_rows, int out_row0, int out_row1, const double *pumping,
+                                       const double *coeffs_host, const double *psi_in, double *psi_out, int halo_rows,
+                                       int up_row0, double *up_dst, int dn_row0, double *dn_dst, void *state,
+                                       void *flags_mine, void *flags_up, void *flags_down, double timeout_seconds,
+                                       nlsb_stream_t stream)
+{
+    if (!pumping || !coeffs_host || !psi_in || !psi_out || psi_in == psi_out || rows_alloc < 1 || cols < 1 || !state || !flags_mine)
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_exchange: bad arguments");
+    if (out_row0 < 0 || out_row1 > rows_alloc || out_row0 > out_row1 || halo_rows < 1)
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_exchange: output rows [%d, %d) outside the slab of %d rows", out_row0,
+                    out_row1, rows_alloc);
+    if ((flags_up && (!up_dst || up_row0 < out_row0 || up_row0 + halo_rows > out_row1)) ||
+        (flags_down && (!dn_dst || dn_row0 < out_row0 || dn_row0 + halo_rows > out_row1)))
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_exchange: the rows a neighbour receives must be rows this step writes");
+    NLSB_TRY(check_coeffs(coeffs_host));
+    NLSB_TRY(check_order_size(global_rows < cols ? global_rows : cols, order));
+    const int path = g_path_2d.load();
+    if (!(path == 8 || (path == 0 && stream_preferred(order, 1, out_row1 - out_row0, cols))))
+        return fail(NLSB_EINVAL, "dev_rk4_step_2d_slab_exchange: this launch would not take the strip-marching kernel "
+                                 "(use nlsb_dev_rk4_step_2d_slab + nlsb_dev_halo_exchange)");
+    CrossWeights w{};
+    NLSB_TRY(weights_from_host(order, wx, wy, &w));
+    const RhsCoeffs shared = rhs_coeffs_from(coeffs_host);
+    PeerStep peer{};
+    const char *out_bytes = reinterpret_cast<const char *>(psi_out);
+    const size_t row_bytes = sizeof(double2) * (size_t)cols;
+    peer.up_row0 = up_row0; peer.dn_row0 = dn_row0; peer.nrows = halo_rows;
+    peer.up_delta = flags_up ? reinterpret_cast<const char *>(up_dst) - (out_bytes + row_bytes * up_row0) : 0;
+    peer.dn_delta = flags_down ? reinterpret_cast<const char *>(dn_dst) - (out_bytes + row_bytes * dn_row0) : 0;
+    peer.state = static_cast<unsigned long long *>(state);
+    peer.flags_mine = static_cast<unsigned long long *>(flags_mine);
+    peer.flags_up = static_cast<unsigned long long *>(flags_up);
+    peer.flags_down = static_cast<unsigned long long *>(flags_down);
+    peer.timeout_cycles = (long long)((timeout_seconds > 0.0 ? timeout_seconds : 5.0) * 1.9e9);
+    Fused2DStep s{1, rows_alloc, cols, global_row0, global_rows, out_row0, out_row1,
+                  reinterpret_cast<const double2 *>(psi_in), reinterpret_cast<double2 *>(psi_out), pumping, nullptr, dt,
+                  &shared};
+    s.peer = &peer;
+    NLSB_TRY(launch_rk4_step_stream_2d(order, s, w, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int nlsb_planar_pitch(int cols) { return cols > 0 ? planar_pitch(cols) : 0; }
 
 int nlsb_dev_rk4_step_2d_slab_planar(int rows_alloc, int cols, int order, double dt, const double *wx,

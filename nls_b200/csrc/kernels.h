@@ -40,6 +40,16 @@ struct Stage2DArgs {
     double dt6;             // dt/6
 };
 int launch_stage_2d(int order, StageMode mode, const CrossWeights &w, const Stage2DArgs &a, cudaStream_t stream);
+// The halo exchange a slab's step launch performs itself (strip-marching kernel, multi-GPU; peer.cu / stream_2d.cu):
+// new psi rows [up_row0, up_row0 + nrows) also go to (address of the local store + up_delta bytes) = the halo rows of
+// the rank above, rows [dn_row0, dn_row0 + nrows) to the rank below; flags as in peer_flags.cuh (null: no neighbour).
+struct PeerStep {
+    long long up_delta, dn_delta;
+    int up_row0, dn_row0, nrows;
+    unsigned long long *state, *flags_mine, *flags_up, *flags_down;
+    long long timeout_cycles;
+};
+
 // fused_2d.cu: one launch advances psi by one full RK4 step (in -> out, distinct buffers).
 struct Fused2DStep {
     int batch, rows, cols;   // local arrays are [batch][rows][cols]
@@ -59,6 +69,7 @@ struct Fused2DStep {
     // TMA, whose row stride must be a multiple of 16 bytes: grids with an odd number of columns hand over a copy of
     // the pumping with an even pitch (api.cu makes it once per time loop)
     int p_pitch = 0;
+    const PeerStep *peer = nullptr;   // strip-marching kernel only: this launch also performs the slab's halo exchange
 };
 // variant 0: 32x32 tiles, two CTAs per SM; variant 1: 32x64 tiles, one CTA of 512 threads per SM
 int launch_rk4_step_fused_2d(int order, int variant, const Fused2DStep &s, const CrossWeights &w, cudaStream_t stream);

@@ -22,6 +22,7 @@
 // in its own memory (the poll never crosses NVLink).
 
 #include "kernels.h"
+#include "peer_flags.cuh"
 
 #include <cstdint>
 
@@ -41,30 +42,6 @@ struct HaloArgs {
     unsigned long long *down;
     long long timeout_cycles;
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// spin until *flag >= epoch; false when the wait timed out
-__device__ bool wait_epoch(const unsigned long long *flag, unsigned long long epoch, long long timeout_cycles)
-{
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flag) < epoch) {
-        if (clock64() - t0 > timeout_cycles) return false;
-        __nanosleep(64);
-    }
-    return true;
-}
-
-constexpr int kReadyFromUp = 0, kReadyFromDown = 8, kDataFromUp = 16, kDataFromDown = 24;   // 64-byte spacing
 
 __global__ void __launch_bounds__(256) halo_exchange_kernel(const HaloArgs a)
 {

@@ -15,6 +15,7 @@
 
 #include "kernels.h"
 #include "stream_2d_core.cuh"
+#include "peer_flags.cuh"
 
 #include <cuda.h>
 #include <atomic>
@@ -51,6 +52,7 @@ struct StreamArgs {
     double dt;
     DiagAcc *diag;           // DIAG: [batch][CTAs per member] partial sums of the entering state's diagnostics
     double area;             // DIAG: area element dx^2
+    PeerStep peer;           // PEER: the halo exchange performed by this launch (kernels.h)
 };
 
 template <int K>
@@ -107,7 +109,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *map, uint3
 // 2-4 (9-14 % slower: the stage 2-4 loads can then no longer be hoisted above the stage-1 arithmetic).
 enum StreamSync { kSyncEvery = 0, kSyncPair = 1 };
 
-template <typename C, bool UNIFORM, int SYNC, bool DIAG>
+// PEER (the last step of a slab's cycle, multi-GPU): this launch IS the halo exchange.
+//   start   CTA 0 publishes READY(e) in both neighbours' flag blocks (my earlier steps, which read my halo rows, are
+//           done: stream order); CTAs whose rows include boundary rows wait for the neighbours' READY(e);
+//   march   stage 4 stores the boundary rows a second time, straight into the neighbours' halo rows (peer-mapped);
+//   end     every CTA fences its stores at system scope and takes a ticket; the last one publishes DATA(e) in the
+//           neighbours' flag blocks, waits for theirs and advances the epoch: when the launch completes, this rank's
+//           halo rows hold the neighbours' new boundary rows.  Waits time out (peer_flags.cuh).
+template <typename C, bool UNIFORM, int SYNC, bool DIAG, bool PEER>
 __global__ void __launch_bounds__(C::T, C::CTAS_PER_SM)
 rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ StreamWeights<C::K> wa,
                   const __grid_constant__ TensorMap map, const __grid_constant__ TensorMap map_p)
@@ -125,7 +134,20 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
     const size_t member = blockIdx.y;
     const size_t plane = (size_t)a.rows * a.cols;
     const Chunk g = make_chunk<C>(strip, chunk, a.chunk_rows, a.out_row0, a.out_row1);
-    const Lane<C> L = make_lane<C>(g, tid, ring, yr, a.out + member * plane, a.rows, a.cols, a.grow0, a.grows, a.dt);
+    Lane<C> L = make_lane<C>(g, tid, ring, yr, a.out + member * plane, a.rows, a.cols, a.grow0, a.grows, a.dt);
+    unsigned long long epoch = 0;
+    if (PEER) {
+        L.up_delta = a.peer.up_delta; L.dn_delta = a.peer.dn_delta;
+        L.up0 = a.peer.up_row0; L.nup = a.peer.flags_up ? a.peer.nrows : 0;
+        L.dn0 = a.peer.dn_row0; L.ndn = a.peer.flags_down ? a.peer.nrows : 0;
+        if (tid == 0) {
+            epoch = a.peer.state[0] + 1;       // the same for every CTA: state[0] changes after the last ticket
+            if (blockIdx.x == 0 && blockIdx.y == 0) {
+                if (a.peer.flags_up) st_release_sys(a.peer.flags_up + kReadyFromDown, epoch);
+                if (a.peer.flags_down) st_release_sys(a.peer.flags_down + kReadyFromUp, epoch);
+            }
+        }
+    }
     RhsCoeffs cl;
     if (!UNIFORM) cl = load_rhs_coeffs(a.coeffs + member * 23);
     const RhsCoeffs &c = UNIFORM ? a.cu : cl;
@@ -145,6 +167,15 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
         for (int b = 0; b < NB && b < g.nbatches; ++b) issue(b);
     }
     for (int i = tid; i < 3 * C::YS * C::YP; i += C::T) yr[i] = make_double2(0.0, 0.0);
+    if (PEER && tid == 0) {
+        // rows this CTA writes into a neighbour's halo: that neighbour must have finished reading them
+        bool ok = true;
+        if (L.nup > 0 && g.r0 < L.up0 + L.nup && g.r1 > L.up0)
+            ok = wait_epoch(a.peer.flags_mine + kReadyFromUp, epoch, a.peer.timeout_cycles) && ok;
+        if (L.ndn > 0 && g.r0 < L.dn0 + L.ndn && g.r1 > L.dn0)
+            ok = wait_epoch(a.peer.flags_mine + kReadyFromDown, epoch, a.peer.timeout_cycles) && ok;
+        if (!ok) atomicAdd(a.peer.state + 2, 1ull);
+    }
     __syncthreads();
 
     State<C> s;
@@ -168,7 +199,7 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
                 const int b = (it + 2 * K) / RB;
                 mbar_wait(bar0 + 8 * (b % NB), (b / NB) & 1);
             }
-            march_iter<C, DIAG, MASKED>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_, &dacc, a.area);
+            march_iter<C, DIAG, MASKED, PEER>(s, L, g, c, wa.wx, wa.wy, it, ph, rh, ro, ph_, po_, &dacc, a.area);
             if ((ph + 1) % PERIOD == 0) {
                 __syncthreads();
                 // thread 0 re-requests the batches whose last reader was one of the iterations this barrier closes:
@@ -201,6 +232,25 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
         __syncthreads();
         const DiagAcc total = diag_block_reduce(dacc, reinterpret_cast<DiagAcc *>(smem_raw));
         if (tid == 0) a.diag[member * gridDim.x + blockIdx.x] = total;
+    }
+    if (PEER) {
+        __threadfence_system();               // this thread's peer stores are visible system-wide ...
+        __syncthreads();                      // ... before the CTA's ticket is taken
+        if (tid == 0) {
+            const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
+            if (atomicAdd(a.peer.state + 1, 1ull) == total - 1) {
+                __threadfence_system();
+                if (a.peer.flags_up) st_release_sys(a.peer.flags_up + kDataFromDown, epoch);
+                if (a.peer.flags_down) st_release_sys(a.peer.flags_down + kDataFromUp, epoch);
+                bool ok = true;
+                if (a.peer.flags_up) ok = wait_epoch(a.peer.flags_mine + kDataFromUp, epoch, a.peer.timeout_cycles) && ok;
+                if (a.peer.flags_down) ok = wait_epoch(a.peer.flags_mine + kDataFromDown, epoch, a.peer.timeout_cycles) && ok;
+                if (!ok) atomicAdd(a.peer.state + 2, 1ull);
+                a.peer.state[1] = 0;
+                __threadfence();
+                a.peer.state[0] = epoch;
+            }
+        }
     }
 }
 
@@ -279,7 +329,7 @@ int cached_map(const MapKey &key, TensorMap *out)
     return 0;
 }
 
-template <typename C, bool UNIFORM, int SYNC, bool DIAG>
+template <typename C, bool UNIFORM, int SYNC, bool DIAG, bool PEER>
 int configure_stream()
 {
     static bool configured[64] = {};
@@ -287,9 +337,9 @@ int configure_stream()
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC, DIAG, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(rk4_stream_kernel<C, UNIFORM, SYNC, DIAG, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         configured[dev] = true;
@@ -359,10 +409,10 @@ StreamPlan plan_shape(int out_rows, int cols, int batch)
     return p;
 }
 
-template <typename C, bool UNIFORM, int SYNC, bool DIAG>
+template <typename C, bool UNIFORM, int SYNC, bool DIAG, bool PEER = false>
 int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
-    int rc = configure_stream<C, UNIFORM, SYNC, DIAG>();
+    int rc = configure_stream<C, UNIFORM, SYNC, DIAG, PEER>();
     if (rc) return rc;
     const int out_rows = s.out_row1 - s.out_row0;
     StreamArgs a{};
@@ -375,6 +425,7 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
     a.dt = s.dt;
     a.diag = static_cast<DiagAcc *>(s.diag_partial);
     a.area = s.diag_area;
+    if (PEER) a.peer = *s.peer;
     StreamWeights<C::K> wa;
     for (int i = 0; i < C::NW; ++i) { wa.wx[i] = w.wx[i]; wa.wy[i] = w.wy[i]; }
     TensorMap map, map_p;
@@ -384,7 +435,7 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
     if (rc) return rc;
     const int chunks = (out_rows + a.chunk_rows - 1) / a.chunk_rows;
     const dim3 grid((unsigned)(a.strips * chunks), (unsigned)s.batch);
-    rk4_stream_kernel<C, UNIFORM, SYNC, DIAG><<<grid, C::T, C::SMEM, stream>>>(a, wa, map, map_p);
+    rk4_stream_kernel<C, UNIFORM, SYNC, DIAG, PEER><<<grid, C::T, C::SMEM, stream>>>(a, wa, map, map_p);
     count_launches(1);
     return (int)cudaGetLastError();
 }
@@ -392,6 +443,10 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
 template <typename C>
 int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
+    if (s.peer) {           // the exchange-carrying step of a slab's cycle: shared coefficients, a single flavour
+        if (!s.uniform || s.diag_partial || s.batch != 1) return fail(NLSB_EINVAL, "the exchange-carrying step takes one grid with shared coefficients");
+        return launch_stream_sync<C, true, kSyncEvery, false, true>(s, w, p, stream);
+    }
     if (s.diag_partial)     // the diagnostics-carrying step of a chunk (one launch in many): a single flavour
         return s.uniform ? launch_stream_sync<C, true, kSyncEvery, true>(s, w, p, stream)
                          : launch_stream_sync<C, false, kSyncEvery, true>(s, w, p, stream);
@@ -497,6 +552,7 @@ int launch_rk4_step_stream_2d(int order, const Fused2DStep &s, const CrossWeight
     // the pumping's tensor map needs a 16-byte row stride and base: callers that cannot provide them (one-off slab
     // steps on grids with an odd number of columns) get the tile kernel -- same bits
     if (!stream_2d_takes(s)) {
+        if (s.peer) return fail(NLSB_EINVAL, "the exchange-carrying step needs the strip-marching kernel (even column count, aligned pumping)");
         if (s.p_pitch && s.p_pitch != s.cols) return fail(NLSB_EINVAL, "a pitched pumping copy must have an even pitch and a 16-byte aligned base");
         return launch_rk4_step_fused_2d(order, 0, s, w, stream);
     }

@@ -115,6 +115,11 @@ struct Lane {
     bool col_in;               // the column lies inside the domain
     bool col_owned;            // ... and inside the strip: this thread writes the new psi
     double half_dt, dt, dt6;
+    // PEER (multi-GPU slabs, last step before a halo exchange): rows [up0, up0 + nup) / [dn0, dn0 + ndn) of the new psi
+    // are ALSO stored into the neighbouring ranks' halo rows, at the address of the local store plus these byte offsets
+    // (peer-mapped memory over NVLink); 0 rows = no such neighbour
+    ptrdiff_t up_delta, dn_delta;
+    int up0, nup, dn0, ndn;
 };
 
 template <class C>
@@ -134,6 +139,8 @@ NLSB_HD Lane<C> make_lane(const Chunk &g, int tid, const double2 *ring, double2 
     const int dhi = rows < grows - grow0 ? rows : grows - grow0;
     L.dspan = dhi > L.dlo ? dhi - L.dlo : 0;
     L.half_dt = dt / 2; L.dt = dt; L.dt6 = dt / 6;
+    L.up_delta = L.dn_delta = 0;
+    L.up0 = L.nup = L.dn0 = L.ndn = 0;
     return L;
 }
 
@@ -222,7 +229,10 @@ NLSB_HD const E *ring_row(const E *rh, const E *ro, int srel)
 // stage-ring stores and the row comparisons -- about a third of the loop's non-FP64 instructions.  On B200 an FP64
 // instruction holds the scheduler's issue port for two cycles and EVERY other instruction for one
 // (tools/micro/fp64_issue.cu), so those instructions are paid for in FP64 throughput.
-template <class C, bool DIAG = false, bool MASKED = true>
+//
+// PEER: see Lane -- the new psi rows a neighbouring rank needs go straight into its halo rows from this kernel's
+// store stage (the halo exchange is the epilogue of the step, not a copy afterwards).
+template <class C, bool DIAG = false, bool MASKED = true, bool PEER = false>
 NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const RhsCoeffs &c, const double (&wx)[C::NW],
                         const double (&wy)[C::NW], int it, int ph, const double2 *rh, const double2 *ro, const double *ph_,
                         const double *po_, DiagAcc *diag = nullptr, double area = 0.0)
@@ -317,7 +327,14 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         double2 v;
         v.x = fma(s.acc[cu].x + k.x, L.dt6, s.psi[cu].x);
         v.y = fma(s.acc[cu].y + k.y, L.dt6, s.psi[cu].y);
-        store_if(s.onext, v, L.col_owned && (unsigned)(r - g.r0) < (unsigned)(g.r1 - g.r0) && (!MASKED || row_in_domain(L, r)));
+        const bool put = L.col_owned && (unsigned)(r - g.r0) < (unsigned)(g.r1 - g.r0) && (!MASKED || row_in_domain(L, r));
+        store_if(s.onext, v, put);
+        if (PEER) {
+            store_if(reinterpret_cast<double2 *>(reinterpret_cast<char *>(s.onext) + L.up_delta), v,
+                     put && (unsigned)(r - L.up0) < (unsigned)L.nup);
+            store_if(reinterpret_cast<double2 *>(reinterpret_cast<char *>(s.onext) + L.dn_delta), v,
+                     put && (unsigned)(r - L.dn0) < (unsigned)L.ndn);
+        }
         s.onext += L.pitch;
     }
 }

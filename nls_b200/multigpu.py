@@ -258,6 +258,26 @@ class _PeerSlab(object):
             C.c_void_p(self.up_flags) if up_plan else null, C.c_void_p(self.down_flags) if dn_plan else null,
             float(timeout_seconds), C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
+    def step_and_exchange(self, src, dst, pumping, row0, row1, dx, dt, order, coeffs, wx, wy, timeout_seconds=5.0):
+        """The last step of a cycle with the halo exchange INSIDE the launch: psi buffer `src` -> `dst` (indices) on
+        local rows [row0, row1); the boundary rows go to the neighbours' halo rows from the kernel's store stage."""
+        p, rb = self.plan, self.row_bytes
+        a_up, _ = p.send_up()
+        a_dn, _ = p.send_down()
+        up_plan = SlabPlan(p.n, p.order, p.rank - 1, p.world, p.halo_steps) if p.up is not None else None
+        dn_plan = SlabPlan(p.n, p.order, p.rank + 1, p.world, p.halo_steps) if p.down is not None else None
+        null = C.c_void_p(None)
+        self._lib.call(
+            "nlsb_dev_rk4_step_2d_slab_exchange", p.rows_alloc, self.cols, int(order), float(dt),
+            wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p), p.global_row0, p.n, int(row0), int(row1),
+            C.c_void_p(pumping.data_ptr()), coeffs.ctypes.data_as(C.c_void_p),
+            C.c_void_p(self.psi_ptr[src]), C.c_void_p(self.psi_ptr[dst]), p.halo,
+            a_up, C.c_void_p(self.up_psi[dst] + up_plan.recv_from_down()[0] * rb) if up_plan else null,
+            a_dn, C.c_void_p(self.down_psi[dst] + dn_plan.recv_from_up()[0] * rb) if dn_plan else null,
+            C.c_void_p(self.state_ptr), C.c_void_p(self.flags_ptr),
+            C.c_void_p(self.up_flags) if up_plan else null, C.c_void_p(self.down_flags) if dn_plan else null,
+            float(timeout_seconds), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
     def status(self):
         """(exchanges completed, waits that timed out) -- synchronises the device."""
         epoch, timeouts = C.c_ulonglong(), C.c_ulonglong()
@@ -286,8 +306,9 @@ class SlabGrid2D(object):
     """
 
     def __init__(self, n, dx, dt, order=5, pumping=None, coeffs=None, u0=0.1, group=None, device=None, stepper=None,
-                 rank=None, world=None, halo_steps=None, exchange=None):
-        """exchange: "peer" (device-initiated exchange over peer-mapped memory, CUDA graphs; default for the CUDA
+                 rank=None, world=None, halo_steps=None, exchange=None, fused_exchange=True):
+        """fused_exchange: let the last step of every cycle carry the halo exchange in its own launch (strip-marching
+        kernel; peer / local exchange only).  exchange: "peer" (device-initiated exchange over peer-mapped memory, CUDA graphs; default for the CUDA
         steppers on interleaved slabs), "nccl" (host-issued isend/irecv through torch.distributed), "local" (peer
         kernels between slabs of ONE process, linked afterwards by ``link_local_peers`` -- tests) or "none"
         (no exchange of its own: ``advance_emulated`` copies the halos)."""
@@ -344,6 +365,8 @@ class SlabGrid2D(object):
             raise ValueError("exchange=%r needs the interleaved CUDA stepper" % exchange)
         self.exchange, self.peer, self.graphs, self.exchange_note = exchange, None, {}, ""
         self.use_graphs = True
+        self.fused_exchange = False
+        self.allow_fused_exchange = fused_exchange
         if exchange in ("peer", "local") and self.world > 1:
             try:
                 self._setup_peer(psi0, local=(exchange == "local"))
@@ -379,6 +402,12 @@ class SlabGrid2D(object):
         # one throw-away step 0 -> 1 over the rows the first real step also writes (same values)
         self.stepper(self.psi[0], self.psi[1], self.pumping, *p.step_rows(0))
         torch.cuda.synchronize(self.device)
+        # does the last step of a cycle take the strip-marching kernel?  Then it carries the exchange itself.
+        from . import _lib
+        lo, hi = p.step_rows(p.halo_steps - 1)
+        out = [C.c_int() for _ in range(4)]
+        _lib.call("nlsb_dev_rk4_2d_plan", 1, hi - lo, self.n, self.order, *[C.byref(v) for v in out])
+        self.fused_exchange = bool(self.allow_fused_exchange and out[0].value == 2 and self.n % 2 == 0)
 
     def _load(self, buf, value, with_halo):
         """Fill a local buffer (owned rows and, from a full array, the halo rows inside the domain)."""
@@ -417,15 +446,21 @@ class SlabGrid2D(object):
     # ---- time stepping -----------------------------------------------------------------------------
     # ---- device-initiated exchange (peer-mapped memory): m steps + one exchange kernel, replayed from a graph --------
     def _peer_step(self):
-        """One RK4 launch on the rows that are still valid, then -- after the m-th step -- the exchange kernel."""
+        """One RK4 launch on the rows that are still valid; the m-th step of a cycle also exchanges the halos -- inside
+        the same launch when the strip-marching kernel takes it (``fused_exchange``), else by the exchange kernel."""
         p = self.plan
-        src, dst = self.psi[self.cur], self.psi[1 - self.cur]
-        self.stepper(src, dst, self.pumping, *p.step_rows(self.since_exchange))
+        last = self.since_exchange + 1 == p.halo_steps
+        rows = p.step_rows(self.since_exchange)
+        if last and self.fused_exchange:
+            wx, wy, coeffs = self.stepper.keepalive
+            self.peer.step_and_exchange(self.cur, 1 - self.cur, self.pumping, rows[0], rows[1], self.dx, self.dt, self.order,
+                                        coeffs, wx, wy)
+        else:
+            self.stepper(self.psi[self.cur], self.psi[1 - self.cur], self.pumping, *rows)
+            if last:
+                self.peer.exchange(1 - self.cur)
         self.cur = 1 - self.cur
-        self.since_exchange += 1
-        if self.since_exchange == p.halo_steps:
-            self.peer.exchange(self.cur)
-            self.since_exchange = 0
+        self.since_exchange = 0 if last else self.since_exchange + 1
         self.steps_done += 1
 
     def _cycle_steps(self):

@@ -51,7 +51,7 @@ def test_slab_parity_size_of_config_4():
 
 
 # ---- device-initiated halo exchange (csrc/peer.cu) ------------------------------------------------------------
-def _run_peer(n, iters, world, order, halo_steps, graphs):
+def _run_peer(n, iters, world, order, halo_steps, graphs, expect_fused=None):
     """Slabs of ONE process linked by plain pointers, every slab on its own stream, halos moved by the product's
     exchange kernel (ready / data flags in device memory) -- what the ranks of a multi-GPU run do over NVLink."""
     from nls_b200.multigpu import (SlabGrid2D, _cuda_stepper_interleaved, advance_emulated_peer, link_local_peers)
@@ -63,6 +63,8 @@ def _run_peer(n, iters, world, order, halo_steps, graphs):
     link_local_peers(slabs)
     for g in slabs:
         g.use_graphs = graphs
+        if expect_fused is not None:
+            assert g.fused_exchange == expect_fused
     advance_emulated_peer(slabs, iters)
     full = np.concatenate([g.local_solution().cpu().numpy() for g in slabs], axis=0)
     status = [g.peer.status() for g in slabs]
@@ -83,11 +85,30 @@ def test_peer_exchange_kernel_matches_single_domain(order, n, iters, world, halo
 
 
 def test_peer_exchange_on_stream_kernel_slabs():
-    """Slabs large enough for the strip-marching kernel (2048 x 2048 over 2 slabs, deep halo 4, graph replay)."""
+    """Slabs large enough for the strip-marching kernel (2048 x 2048 over 2 slabs, deep halo 4, graph replay): the last
+    step of every cycle carries the exchange in its own launch (stores into the neighbour's halo rows + flags)."""
     single, _, _ = _run(2048, 9, 1)
-    full, status = _run_peer(2048, 9, 2, 5, 4, True)
+    full, status = _run_peer(2048, 9, 2, 5, 4, True, expect_fused=True)
     assert np.array_equal(full, single)
     assert all(t == 0 and e == 2 for e, t in status)
+
+
+@pytest.mark.parametrize("order,n,iters,world,halo_steps,graphs", [
+    (5, 256, 24, 2, 1, False), (5, 256, 24, 2, 1, True), (5, 384, 26, 4, 4, True), (3, 160, 20, 4, 2, True),
+    (7, 288, 12, 2, 2, True), (5, 260, 21, 3, 1, True), (5, 512, 17, 8, 2, True)])
+def test_exchange_inside_the_step_launch_matches_single_domain(order, n, iters, world, halo_steps, graphs):
+    """The exchange-carrying step (strip-marching kernel forced on small slabs): READY / DATA flags, peer stores from
+    the store stage, epoch counter advanced by the launch itself -- ragged slabs, 2..8 ranks, every order."""
+    from nls_b200.engine import set_2d_path
+    single, _, _ = _run(n, iters, 1, order)
+    try:
+        set_2d_path("stream")
+        full, status = _run_peer(n, iters, world, order, halo_steps, graphs, expect_fused=True)
+    finally:
+        set_2d_path("auto")
+    assert np.array_equal(full, single)
+    for epoch, timeouts in status:
+        assert timeouts == 0 and epoch == iters // halo_steps
 
 
 def test_peer_exchange_between_processes():
