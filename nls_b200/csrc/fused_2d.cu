@@ -218,6 +218,7 @@ __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, 
                     double ar = lre[j][i], ai = lim[j][i];   // rows j-K .. j-1 have already contributed
 #pragma unroll
                     for (int tp = -K; tp <= K; ++tp) {
+                        if (tp == 0) continue;        // the centre tap is folded into the pointwise part (rhs_point_c)
                         ar = fma(wx[tp + K], xr[2 * PH + i + tp], ar);
                         ai = fma(wx[tp + K], xi[2 * PH + i + tp], ai);
                     }
@@ -275,7 +276,7 @@ __device__ __forceinline__ void micro_tile(const Smem<C> &sm, const TileCtx &t, 
         double yr[2], yi[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const double2 k = rhs_point(c, cpv[i], make_double2(cre[j][i], cim[j][i]), lre[j][i], lim[j][i]);
+            const double2 k = rhs_point_c(c, cpv[i], make_double2(cre[j][i], cim[j][i]), wx[K], lre[j][i], lim[j][i]);
             const bool inside = rowin && (i ? colin1 : colin0);
             if (S < 4) {
                 const double cy = (S == 3) ? t.dt : t.half_dt;

@@ -100,18 +100,23 @@ rk4_1d_resident(int n, int iters, double dt, const double *__restrict__ taps, co
 
 #pragma unroll
             for (int p = 0; p < PPT; ++p) {
-                double lr = 0.0, li = 0.0;
+                // the operator row WITHOUT its centre tap: rhs_point_c folds that one into the pointwise part
+                double lr = 0.0, li = 0.0, tap0 = 0.0;
 #pragma unroll
                 for (int t = 0; t < M; ++t) {
                     // large systems re-read their operator rows through L1 instead of pinning registers
                     const double a = TAPS_IN_REGS ? tap[p][t] : (live[p] ? __ldg(taps + (size_t)(i0 + p) * M + t) : 0.0);
+                    if (t == K) {
+                        tap0 = a;
+                        continue;
+                    }
                     lr = fma(a, w[p + t].x, lr);
                     li = fma(a, w[p + t].y, li);
                 }
                 // Nodes beyond the end of the system need no mask: their psi, c12*P and operator rows are zero, so their k is
                 // exactly zero (rhs_point of zeros) and they stay zero -- the right edge sees the truncated band matrix.
                 // (On B200 every non-FP64 instruction costs this FP64-bound loop an issue cycle: tools/micro/fp64_issue.cu.)
-                const double2 k = rhs_point(c, cp[p], w[K + p], lr, li);
+                const double2 k = rhs_point_c(c, cp[p], w[K + p], tap0, lr, li);
                 if (DIAG && s == 0 && it == iters - 1 && live[p]) {
                     const int i = i0 + p;
                     diag_accumulate(dacc, c, cp[p], w[K + p], k, ((double)(i + 1) - 1.0) * dx,      // nls.f90:940-947

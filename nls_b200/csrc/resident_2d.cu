@@ -113,7 +113,7 @@ rk4_resident_2d_kernel(const __grid_constant__ ResidentArgs a, const __grid_cons
                     im[n] = packet_read(src[n] + par + 1);
                 }
         }
-        phase_a<C>(s, c, cp_plane, x, r0);
+        phase_a<C>(s, c, cp_plane, x, r0, wa.wx[C::K]);
         if (!first) {
             const long long t0 = clock64();
             for (;;) {

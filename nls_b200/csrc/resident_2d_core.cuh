@@ -232,10 +232,10 @@ NLSB_HD Packet *mailbox_cell(Packet *mail, int patch, int par, int cell)
 
 // Phase A: the coefficients a, b of the thread's nodes from the stage input y (registers only).
 template <class C>
-NLSB_HD void phase_a(State<C> &s, const RhsCoeffs &c, const double *cp_plane, int x, int r0)
+NLSB_HD void phase_a(State<C> &s, const RhsCoeffs &c, const double *cp_plane, int x, int r0, double w0)
 {
 #pragma unroll
-    for (int i = 0; i < C::RT; ++i) rhs_ab(c, cp_plane[(r0 + i) * C::TX + x], s.y[i], s.a[i], s.b[i]);
+    for (int i = 0; i < C::RT; ++i) rhs_abm(c, cp_plane[(r0 + i) * C::TX + x], s.y[i], w0, s.a[i], s.b[i]);   // b holds b - w0
 }
 
 // Phase B of stage S (1..4) for the thread owning column x, rows r0 .. r0 + RT - 1 of patch p.
@@ -274,7 +274,8 @@ NLSB_HD void phase_b(State<C> &s, const Patch &p, int x, int r0, double2 *psi_pl
         }
 #pragma unroll
         for (int tp = -K; tp <= K; ++tp) {
-            const double2 v = tp == 0 ? ext[i + K] : line[tp];
+            if (tp == 0) continue;          // the centre tap is folded into b (rhs_abm)
+            const double2 v = line[tp];
             lr = fma(wx[tp + K], v.x, lr);
             li = fma(wx[tp + K], v.y, li);
         }

@@ -177,6 +177,10 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
         if (!ok) atomicAdd(a.peer.state + 2, 1ull);
     }
     __syncthreads();
+    // warps whose frame columns all lie to the right of the domain have nothing to compute (active_threads): they
+    // leave here, after their share of the set-up (the later barriers wait for the non-exited threads of the CTA
+    // only).  The diagnostics flavour keeps them for its CTA-wide reduction.
+    if (!DIAG && tid >= active_threads<C>(g, a.cols)) return;
 
     State<C> s;
     DiagAcc dacc = diag_zero();
@@ -388,7 +392,12 @@ StreamPlan plan_shape(int out_rows, int cols, int batch)
 {
     StreamPlan p{C::T, (cols + C::W - 1) / C::W, C::chunk_rows(140), kSyncEvery, 0.0};
     p.sync = (C::T <= 128 && C::K >= 2) ? kSyncPair : kSyncEvery;
-    const double per_iter = (double)C::T * C::CTAS_PER_SM * shape_cost(C::K, C::T);
+    // the last strip keeps only the warps whose columns lie inside the domain (active_threads): an SM's time goes with
+    // the warps it runs, so the swept columns per row of strips are (strips - 1) T + the last strip's active threads
+    const int last_need = cols - (p.strips - 1) * C::W + C::HALO;
+    const int last_active = last_need < C::T ? (last_need + 31) / 32 * 32 : C::T;
+    const double swept = ((double)(p.strips - 1) * C::T + last_active) / ((double)p.strips * C::T);
+    const double per_iter = (double)C::T * C::CTAS_PER_SM * shape_cost(C::K, C::T) * swept;
     const long long slots = (long long)sm_count() * C::CTAS_PER_SM;      // CTAs resident at once
     const int forced = g_tune_iters.load();                              // tuning knob: iterations per CTA
     const int m_lo = forced >= 6 * C::K + C::U ? (forced + C::U - 1) / C::U : (6 * C::K) / C::U + 2;

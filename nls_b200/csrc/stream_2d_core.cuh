@@ -94,6 +94,19 @@ NLSB_HD Chunk make_chunk(int strip, int chunk, int rows_per_chunk, int out_row0,
     return g;
 }
 
+// Threads of a strip that have work.  The frame columns to the right of the domain's last column hold zeros in every
+// stage (truncated stencil): the TMA fills them with zeros in the psi ring and the stage rings keep the zeros they
+// are initialised with when nobody writes them, so the warps that would own only such columns leave right after the
+// set-up.  Only the LAST strip of a row of strips is narrower than T: a 1024-column member cut into 112-column
+// strips ends in a strip of 16 columns = one warp of 128 threads (1184 swept columns per row instead of 1280).
+template <class C>
+NLSB_HD int active_threads(const Chunk &g, int cols)
+{
+    const int in_domain = cols - (g.c0 - C::HALO);          // frame columns [0, in_domain) lie left of the domain's end
+    const int need = in_domain < C::T ? in_domain : C::T;
+    return (need + 31) / 32 * 32;
+}
+
 // What a thread keeps in registers for the whole march.
 template <class C>
 struct State {
@@ -160,8 +173,9 @@ NLSB_HD void store_if(double2 *p, double2 v, bool put)
 #endif
 }
 
-// Cross stencil of one node: y taps from the register window `w` (period PER, centre index CI), x taps from `xn`
-// (xn[K] is the centre).  Order of the chain: the K rows above, the 2K+1 x taps, the K rows below (fused_2d.cu).
+// Cross stencil of one node WITHOUT its centre tap (rhs_point_c folds wx[K] into the pointwise part): y taps from the
+// register window `w` (period PER, centre index CI), x taps from `xn` (xn[K], the centre, is not read).  Order of
+// the chain: the K rows above, the 2K x taps, the K rows below (fused_2d.cu).
 template <class C, int PER>
 NLSB_HD void cross_stencil(const double2 (&w)[PER], int ci, const double2 (&xn)[C::NW], const double (&wx)[C::NW],
                            const double (&wy)[C::NW], double &lr, double &li)
@@ -176,6 +190,7 @@ NLSB_HD void cross_stencil(const double2 (&w)[PER], int ci, const double2 (&xn)[
     }
 #pragma unroll
     for (int tp = 0; tp < C::NW; ++tp) {
+        if (tp == K) continue;
         lr = fma(wx[tp], xn[tp].x, lr);
         li = fma(wx[tp], xn[tp].y, li);
     }
@@ -268,10 +283,9 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         const int ci = (ph + 3 * K) % U;
         s.cp[ci] = c.c12 * *ring_row<C>(ph_, po_, ph + K);    // c12 * P(j), rounded once (nls.f90:580 association)
         const double2 u = s.psi[ci];
-        x1[K] = u;
         double lr, li;
         cross_stencil<C, U>(s.psi, ci, x1, wx, wy, lr, li);
-        const double2 k = rhs_point(c, s.cp[ci], u, lr, li);
+        const double2 k = rhs_point_c(c, s.cp[ci], u, wx[K], lr, li);
         if (DIAG) {
             if (L.col_owned && (unsigned)(j - g.r0) < (unsigned)(g.r1 - g.r0) && (!MASKED || row_in_domain(L, j)))
                 diag_accumulate(*diag, c, s.cp[ci], u, k, 1.0, area);
@@ -287,10 +301,9 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
     {
         const int ci = (ph + K) % NW, cu = (ph + 2 * K) % U;
         const double2 u = s.y2[ci];
-        x2[K] = u;
         double lr, li;
         cross_stencil<C, NW>(s.y2, ci, x2, wx, wy, lr, li);
-        const double2 k = rhs_point(c, s.cp[cu], u, lr, li);
+        const double2 k = rhs_point_c(c, s.cp[cu], u, wx[K], lr, li);
         double2 y;
         y.x = in2 ? fma(k.x, L.half_dt, s.psi[cu].x) : 0.0;
         y.y = in2 ? fma(k.y, L.half_dt, s.psi[cu].y) : 0.0;
@@ -303,10 +316,9 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
     {
         const int ci = (ph + K) % NW, cu = (ph + K) % U;
         const double2 u = s.y3[ci];
-        x3[K] = u;
         double lr, li;
         cross_stencil<C, NW>(s.y3, ci, x3, wx, wy, lr, li);
-        const double2 k = rhs_point(c, s.cp[cu], u, lr, li);
+        const double2 k = rhs_point_c(c, s.cp[cu], u, wx[K], lr, li);
         double2 y;
         y.x = in3 ? fma(k.x, L.dt, s.psi[cu].x) : 0.0;
         y.y = in3 ? fma(k.y, L.dt, s.psi[cu].y) : 0.0;
@@ -320,10 +332,9 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         const int ci = (ph + K) % NW, cu = ph % U;
         const int r = j - 3 * K;
         const double2 u = s.y4[ci];
-        x4[K] = u;
         double lr, li;
         cross_stencil<C, NW>(s.y4, ci, x4, wx, wy, lr, li);
-        const double2 k = rhs_point(c, s.cp[cu], u, lr, li);
+        const double2 k = rhs_point_c(c, s.cp[cu], u, wx[K], lr, li);
         double2 v;
         v.x = fma(s.acc[cu].x + k.x, L.dt6, s.psi[cu].x);
         v.y = fma(s.acc[cu].y + k.y, L.dt6, s.psi[cu].y);

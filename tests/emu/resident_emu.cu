@@ -106,7 +106,7 @@ static int run(int batch, int rows, int cols, long long capacity, int steps, uns
         const int S = t.stage % 4 + 1;
         const bool last = t.stage == total - 1;
         double2 *o = last ? result.data() + t.p.member * plane : nullptr;
-        for (int tid = 0; tid < C::T; ++tid) phase_a<C>(t.st[tid], c, t.cp.data(), tid % C::TX, (tid / C::TX) * C::RT);
+        for (int tid = 0; tid < C::T; ++tid) phase_a<C>(t.st[tid], c, t.cp.data(), tid % C::TX, (tid / C::TX) * C::RT, wx[C::K]);
         for (int tid = 0; tid < C::T; ++tid) {
             const int x = tid % C::TX, r0 = (tid / C::TX) * C::RT;
             State<C> &s = t.st[tid];

@@ -49,7 +49,8 @@ static int run(int rows, int cols, int grow0, int grows, int out_row0, int out_r
             std::vector<State<C>> st(C::T);
             std::vector<Lane<C>> lane(C::T);
             for (int b = 0; b < C::NB && b < g.nbatches; ++b) fill_batch<C>(ring, pring.data(), g, b, in, P, rows, cols);
-            for (int t = 0; t < C::T; ++t) {
+            const int nact = active_threads<C>(g, cols);      // the warps right of the domain leave (as in the kernel)
+            for (int t = 0; t < nact; ++t) {
                 lane[t] = make_lane<C>(g, t, ring, yr.data(), out, rows, cols, grow0, grows, dt);
                 march_begin<C>(st[t], lane[t], g);
             }
@@ -59,7 +60,7 @@ static int run(int rows, int cols, int grow0, int grows, int out_row0, int out_r
                     highest_waited = (it + 2 * C::K) / C::RB;
                     if (highest_waited >= g.nbatches) return 1;     // the kernel would wait for a batch never issued
                 }
-                for (int t = 0; t < C::T; ++t) {
+                for (int t = 0; t < nact; ++t) {
                     const int half = (it / C::U) & 1;
                     march_iter<C>(st[t], lane[t], g, c, wx, wy, it, it % C::U, ring + half * C::U * C::T + t,
                                   ring + (half ^ 1) * C::U * C::T + t, pring.data() + half * C::U * C::T + t,
