@@ -254,6 +254,31 @@ def cpu_sample(w, kind="sp", budget_s=15.0):
     return per_step * s / dt, dt, sample
 
 
+def cpu_all_cores(w, budget_s=6.0):
+    """What the box's host cores deliver when EVERY core runs its own independent grid with the serial sp oracle (the
+    way schedulr farms parameter points out; one grid cannot use more than one thread in the reference): one 1024^2
+    crop (or the whole member if smaller / 1D) per core, the same number of RK steps each.  Reported beside the serial
+    figure, never instead of it."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    P, c, u0, n = w["pumping"][0], w["coeffs"][0], w["u0"][0], w["n"]
+    if w["dim"] == 2 and n > 1024:
+        lo = (n - 1024) // 2
+        P, u0, n = np.ascontiguousarray(P[lo:lo + 1024, lo:lo + 1024]), np.ascontiguousarray(u0[lo:lo + 1024, lo:lo + 1024]), 1024
+    per_step = n if w["dim"] == 1 else n * n
+    s = int(max(1, min(w["iters"], budget_s * CPU_RATE_GUESS // per_step)))
+    fn = O.sp.solve_nls if w["dim"] == 1 else O.sp.solve_nls_2d
+    jobs = [(np.array(P), np.array(u0)) for _ in range(cores)]          # private copies: no shared pages
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as pool:                            # ctypes releases the GIL during the call
+        list(pool.map(lambda j: fn(w["dt"], w["dx"], w["order"], s, j[0], c, j[1]), jobs))
+    dt = time.perf_counter() - t0
+    return {"value": cores * per_step * s / dt, "unit": UNIT, "cores": cores,
+            "sample": "%d independent %s grids (one per core), %d RK steps each, sp oracle" %
+                      (cores, "%dx%d" % (n, n) if w["dim"] == 2 else "n=%d" % n, s)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -278,7 +303,7 @@ def run_reference(args):
                    "note": "the reference algorithm is serial (no threads in nls.f90): one bounded sample per step, "
                            "normalised per point-step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count()},
+                         "host_cores": os.cpu_count(), "all_cores_independent_grids": cpu_all_cores(w)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -362,7 +387,7 @@ def measure(env, args, name, steps, warmup, iters=None, warmup_iters=None, with_
     if slabs:
         from nls_b200.multigpu import SlabGrid2D
         eng = SlabGrid2D(w["n"], w["dx"], w["dt"], w["order"], w["pumping"][0], w["coeffs"][0], w["u0"][0], device=dev,
-                         exchange=args.exchange)
+                         exchange=args.exchange, halo_steps=args.halo_steps, fused_exchange=args.fused_exchange != "off")
         state = lambda: eng.state_buffer()
     elif w["dim"] == 1:
         eng = Ensemble1D(w["n"], w["dx"], w["dt"], order=w["order"], batch=w["batch"], pumping=w["pumping"],
@@ -417,7 +442,11 @@ def measure(env, args, name, steps, warmup, iters=None, warmup_iters=None, with_
         partition = ("row slabs (strong scaling), %d-row halos, one exchange per %d RK steps, %s; %.1f %% of a rank's rows "
                      "recomputed redundantly between exchanges"
                      % (eng.plan.halo, eng.plan.halo_steps,
-                        {"peer": "device-initiated exchange kernel over peer-mapped memory (NVLink), m-step cycle in a CUDA graph",
+                        {"peer": ("device-initiated exchange over peer-mapped memory (NVLink) carried by the last step launch of "
+                                  "every cycle (boundary rows stored into the neighbours' halo rows by the step kernel's store "
+                                  "stage, READY / DATA flags in device memory), m-step cycle in a CUDA graph"
+                                  if getattr(eng, "fused_exchange", False) else
+                                  "device-initiated exchange kernel over peer-mapped memory (NVLink), m-step cycle in a CUDA graph"),
                          "nccl": "host-issued NCCL isend/irecv"}[eng.exchange] + ((" [" + eng.exchange_note + "]") if eng.exchange_note else ""),
                         100.0 * eng.plan.step_halo * (eng.plan.halo_steps - 1) / max(eng.plan.rows_local, 1)))
     else:
@@ -445,6 +474,7 @@ def measure(env, args, name, steps, warmup, iters=None, warmup_iters=None, with_
         rec["roofline"]["avg_launch_us_note"] = "step time of the slowest rank / RK steps: includes its share of the exchange kernel"
         epoch, timeouts = eng.peer.status() if eng.peer is not None else (None, 0)
         rec["config"]["halo_exchanges_total"] = epoch
+        rec["config"]["exchange_in_step_launch"] = bool(getattr(eng, "fused_exchange", False))
         rec["config"]["halo_wait_timeouts"] = timeouts
     archived = ncu_record(name) if (args.path == "auto" and not slabs) else None
     rec["roofline"]["traffic"] = archived.get("dram_bytes_per_launch") if archived else None
@@ -551,7 +581,8 @@ def run_engine(args):
             rate, dt_cpu, sample = cpu_sample(wc, "sp", budget_s=15.0)
             rate_dp, _, sample_dp = cpu_sample(wc, "dp", budget_s=4.0)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                                    "host_cores": os.cpu_count(), "dp_value": rate_dp, "dp_sample": sample_dp}
+                                    "host_cores": os.cpu_count(), "dp_value": rate_dp, "dp_sample": sample_dp,
+                                    "all_cores_independent_grids": cpu_all_cores(wc)}
         print(json.dumps(line))
     if env.world > 1:
         env.dist.barrier()
@@ -575,6 +606,9 @@ def main():
     ap.add_argument("--order", type=int, default=None, help="override the stencil order (profiling only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default=None, help="halo transport of the slab run (default: peer)")
+    ap.add_argument("--fused-exchange", choices=["on", "off"], default="on", help="slab run: the last step launch of a cycle carries "
+                    "the halo exchange (on, default) or a separate exchange kernel follows it (off)")
+    ap.add_argument("--halo-steps", type=int, default=None, help="slab run: RK steps between two halo exchanges (default: the plan's)")
     ap.add_argument("--path", choices=["auto", "fused", "fused32", "fused64", "tma32", "tma64", "tma32_persistent", "tma64_persistent", "stream", "resident", "staged"], default="auto", help="2D kernel family")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
