@@ -567,7 +567,9 @@ def run_engine(args):
     line["also"] = {}
     for other in also:
         # shorter warm-up passes for the whole-horizon 1D launch; one timed pass of C3 is 6 s on one GPU
-        sub_steps = {"c2": 3, "c3": 1, "c5": 3, "c1": 3, "c4": 2}[other]
+        # sharded sub-records get more timed passes as the ranks' shares shrink: >= 1 s per timed region, so that the
+        # 20 ms clock sampler sees it
+        sub_steps = {"c2": 3, "c3": 1 if env.world < 4 else 2, "c5": 3 * env.world, "c1": 3, "c4": 2}[other]
         warm_iters = {"c3": 500}.get(other)
         sub = measure(env, args, other, sub_steps, 3, warmup_iters=warm_iters)
         line["also"][other] = {"value": sub["value"], "unit": UNIT, "frac": sub["roofline"]["frac"],
