@@ -148,6 +148,49 @@ diagnostics_1d_kernel(int n, double dx, const double *__restrict__ taps, const d
     if (threadIdx.x == 0) emit(a, member, partial, out8);
 }
 
+// Large ensembles of short systems (C3: 65 536 x 1000): ONE WARP per member -- nodes strided over the lanes (coalesced
+// 512-byte loads), a shuffle reduction and no barrier, eight members per CTA -- instead of a CTA per member whose 256
+// threads see four nodes each and then pay a block reduction.
+template <int M>
+__global__ void __launch_bounds__(kThreads)
+diagnostics_1d_warp_kernel(int batch, int n, double dx, const double *__restrict__ taps, const double *__restrict__ pumping,
+                           const double *__restrict__ coeffs, const double2 *__restrict__ u, double *__restrict__ out8)
+{
+    constexpr int K = (M - 1) / 2;
+    const int lane = threadIdx.x & 31;
+    const size_t member = (size_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (member >= (size_t)batch) return;                   // whole warps leave: no barrier below
+    const double2 *um = u + member * n;
+    const double *P = pumping + member * n;
+    const RhsCoeffs c = load_rhs_coeffs(coeffs + member * 23);
+    const double ring = n > 1 ? (n * dx) / (n - 1) : 0.0;
+    Acc a = acc_zero();
+    for (int i = lane; i < n; i += 32) {
+        double lr = 0.0, li = 0.0;
+#pragma unroll
+        for (int t = 0; t < M; ++t) {
+            const int j = i + t - K;
+            if (j >= 0 && j < n) {
+                const double tap = taps[(size_t)i * M + t];
+                lr = fma(tap, um[j].x, lr);
+                li = fma(tap, um[j].y, li);
+            }
+        }
+        const double cp = c.c12 * P[i];
+        const double w = ((double)(i + 1) - 1.0) * dx;
+        const double wd = 6.283185307179586 * (i * ring) * dx;
+        accumulate(a, c, cp, um[i], rhs_point(c, cp, um[i], lr, li), w, wd);
+    }
+    a = diag_warp_reduce(a);
+    if (lane == 0) {
+        double *o = out8 + member * 8;
+#pragma unroll
+        for (int i = 0; i < kSums; ++i) o[i] = a.s[i];
+        o[6] = a.m[0];
+        o[7] = a.m[1];
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 finish_diagnostics_kernel(int nparts, const Acc *__restrict__ partial, double *__restrict__ out8)
 {
@@ -226,6 +269,17 @@ int launch_diagnostics_1d(int batch, int n, int order, double dx, const double *
                           const double *coeffs, const double2 *u, void *scratch, double *out8, cudaStream_t stream)
 {
     const int parts = parts_for(((size_t)n + kThreads - 1) / kThreads, batch);
+    if (parts == 1 && batch >= 8 * 592 && n <= 4096) {      // a warp per member keeps every SM busy and needs no barrier
+        const unsigned ctas = (unsigned)((batch + kThreads / 32 - 1) / (kThreads / 32));
+        switch (order) {
+        case 3: diagnostics_1d_warp_kernel<3><<<ctas, kThreads, 0, stream>>>(batch, n, dx, taps, pumping, coeffs, u, out8); break;
+        case 5: diagnostics_1d_warp_kernel<5><<<ctas, kThreads, 0, stream>>>(batch, n, dx, taps, pumping, coeffs, u, out8); break;
+        case 7: diagnostics_1d_warp_kernel<7><<<ctas, kThreads, 0, stream>>>(batch, n, dx, taps, pumping, coeffs, u, out8); break;
+        default: return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+        }
+        count_launches(1);
+        return (int)cudaGetLastError();
+    }
     const dim3 grid((unsigned)batch, (unsigned)parts);
     Acc *partial = static_cast<Acc *>(scratch);
     switch (order) {
