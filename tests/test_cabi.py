@@ -133,7 +133,7 @@ def test_kernel_choice_and_stream_geometry_for_the_baseline_configs():
     # outweighs their wider relative halo on the 8192-column grid; a 1024-column member is cut into 4 x 240 + 64 columns
     # (the last strip keeps 3 of its 8 warps: 1120 swept columns) rather than 9 x 112 + 16 (1184) -- measured 6.49e10
     # against 6.17e10 node-steps/s; order 3 keeps 256, order 7 has a single shape
-    assert plan(256, 1024)[1:3] == [256, 5] and plan(1, 8192)[1:3] == [128, 74]
+    assert plan(256, 1024)[1:3] == [256, 5] and plan(1, 8192)[1:] == [128, 74, 2048]      # 74 x 4 CTAs: one wave
     assert plan(1, 4096, 3)[1] == 256 and plan(1, 4096, 7)[1] == 192
     # a 1024-row slab of the 8192-column grid with its deep halo (multi-GPU): exactly one wave of 2 x 148 CTAs
     out = [C.c_int() for _ in range(4)]

@@ -194,6 +194,35 @@ def test_device_diagnostics_match_host_formulas(order):
     assert all(np.array_equal(again[k], d[k]) for k in d)           # fixed reduction tree: reproducible
 
 
+@pytest.mark.parametrize("order,n", [(5, 100), (3, 37), (7, 333)])
+def test_device_diagnostics_of_a_large_ensemble_use_a_warp_per_member(order, n):
+    """Ensembles of >= 4736 short systems take the warp-per-member kernel (diagnostics.cu): sampled members against
+    the host formulas (1e-12), every member against the CTA-per-member kernel through a small ensemble of copies, and
+    reproducible bits.  n = 37 leaves lanes without a node in the last round, n = 333 is not a multiple of 32."""
+    from nls_b200.engine import Ensemble1D
+    B = 5000
+    m = model_1d(n, order=order)
+    rng = np.random.default_rng(n)
+    scale = 0.5 + rng.random(B)
+    u = (rough_field(n, 7) * 0.3 + 0.2)[None, :] * scale[:, None]
+    P = m.getPumping()[None, :] * (0.5 + rng.random(B))[:, None]
+    e = Ensemble1D(n, m.dx, m.dt, order=order, batch=B, pumping=P, coeffs=m.getCoefficients(), u0=u)
+    d = e.diagnostics()
+    keys = ("chemical_potential", "damping_integral", "particles", "max_density", "max_reservoir")
+    for b in (0, 1, 7, 8, 2499, B - 1):
+        m.setPumping(lambda *grid, profile=P[b]: profile)
+        want = _host_diagnostics(m, u[b], order, 1)
+        for k, w_ in zip(keys, want):
+            assert abs(d[k][b] - w_) <= 1e-12 * max(abs(w_), 1.0), (order, b, k)
+    pick = np.arange(0, B, 97)
+    small = Ensemble1D(n, m.dx, m.dt, order=order, batch=len(pick), pumping=P[pick], coeffs=m.getCoefficients(), u0=u[pick])
+    ds = small.diagnostics()                                   # CTA-per-member kernel: another summation order
+    for k in keys:
+        assert np.all(np.abs(d[k][pick] - ds[k]) <= 1e-12 * np.maximum(np.abs(ds[k]), 1.0)), k
+    again = e.diagnostics()
+    assert all(np.array_equal(again[k], d[k]) for k in d)
+
+
 def test_continuation_with_changing_pumping_equals_fresh_solves():
     """psi stays on the device across chunks while the pump changes (animation / check loops)."""
     from nls_b200.engine import Grid2D
