@@ -191,9 +191,10 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
     const double2 *rh = ring + tid, *ro = ring + U * C::T + tid;
     const double *ph_ = pring + tid, *po_ = pring + U * C::T + tid;
     // One unrolled block of U iterations, with or without the domain masks (see march_iter): a block needs them when
-    // the strip touches the left / right edge of the domain (some frame column within 3K of the strip lies outside)
-    // or when one of the rows j - 3K .. j of its iterations lies outside -- the first / last blocks of the chunks at
-    // the top and bottom of the domain.  Both bodies are compiled; the choice is uniform over the CTA.
+    // one of the rows j - 3K .. j of its iterations lies outside the domain -- the first / last blocks of the chunks
+    // at the top and bottom of the domain (columns outside the domain are handled by predicated ring stores in both
+    // bodies, so the edge strips run the mask-free body too; measured: no difference on 8192^2, one rule less).
+    // Both bodies are compiled; the choice is uniform over the CTA.
     auto block = [&](auto masked_tag, int itb) {
         constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
@@ -219,12 +220,10 @@ rk4_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ 
             }
         }
     };
-    const int used_c0 = g.c0 - C::SKEW, used_c1 = g.c0 + C::W + C::SKEW;      // columns whose stage values are used
-    const bool edge_strip = used_c0 < 0 || used_c1 > a.cols;
     const int row_lo = L.dlo, row_hi = L.dlo + L.dspan;
     for (int itb = 0; itb < g.niter; itb += U) {
         const int j0 = g.jstart + itb;                                             // stage-1 row of the block's first iteration
-        if (edge_strip || j0 - C::SKEW < row_lo || j0 + U > row_hi)
+        if (j0 - C::SKEW < row_lo || j0 + U > row_hi)
             block(std::true_type{}, itb);
         else
             block(std::false_type{}, itb);

@@ -238,10 +238,13 @@ NLSB_HD const E *ring_row(const E *rh, const E *ro, int srel)
 // potential sums, damping integral, particle number, peak density / reservoir: diag_acc.cuh) are accumulated there
 // for the nodes this CTA produces -- no extra pass over the field, no stencil evaluated twice.
 //
-// MASKED = false: the caller guarantees that every node this iteration evaluates for later use lies inside the
-// domain (rows j - 3K .. j of an interior block of iterations, all frame columns of an interior strip), so the
-// "zero outside the domain" selects vanish: per iteration 12 FSEL, the register moves that feed their results to the
-// stage-ring stores and the row comparisons -- about a third of the loop's non-FP64 instructions.  On B200 an FP64
+// MASKED = false: the caller guarantees that every ROW this iteration evaluates for later use lies inside the domain
+// (rows j - 3K .. j of an interior block of iterations), so the "zero outside the domain" selects vanish: per
+// iteration 12 FSEL, the register moves that feed their results to the stage-ring stores and the row comparisons --
+// about a third of the loop's non-FP64 instructions.  COLUMNS outside the domain (the left halo of the first strip,
+// the tail of the last) need no select either: a thread that owns one simply never publishes -- its stage-ring
+// entries keep the zeros the rings are initialised with, which is what its in-domain neighbours must read, and
+// whatever it computes for itself is never stored (predicated STS: no extra instruction).  On B200 an FP64
 // instruction holds the scheduler's issue port for two cycles and EVERY other instruction for one
 // (tools/micro/fp64_issue.cu), so those instructions are paid for in FP64 throughput.
 //
@@ -295,7 +298,7 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         y.y = in1 ? fma(k.y, L.half_dt, u.y) : 0.0;
         s.acc[ci] = k;
         s.y2[(ph + 2 * K) % NW] = y;
-        L.yr[(0 * C::YS + q) * YP + K + L.fx] = y;
+        if (MASKED || L.col_in) L.yr[(0 * C::YS + q) * YP + K + L.fx] = y;     // see MASKED below: outside columns stay zero
     }
     // ---- stage 2, row j - K ---------------------------------------------------------------------------
     {
@@ -310,7 +313,7 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         s.acc[cu].x = fma(2.0, k.x, s.acc[cu].x);
         s.acc[cu].y = fma(2.0, k.y, s.acc[cu].y);
         s.y3[(ph + 2 * K) % NW] = y;
-        L.yr[(1 * C::YS + q) * YP + K + L.fx] = y;
+        if (MASKED || L.col_in) L.yr[(1 * C::YS + q) * YP + K + L.fx] = y;     // see MASKED below: outside columns stay zero
     }
     // ---- stage 3, row j - 2K --------------------------------------------------------------------------
     {
@@ -325,7 +328,7 @@ NLSB_HD void march_iter(State<C> &s, const Lane<C> &L, const Chunk &g, const Rhs
         s.acc[cu].x = fma(2.0, k.x, s.acc[cu].x);
         s.acc[cu].y = fma(2.0, k.y, s.acc[cu].y);
         s.y4[(ph + 2 * K) % NW] = y;
-        L.yr[(2 * C::YS + q) * YP + K + L.fx] = y;
+        if (MASKED || L.col_in) L.yr[(2 * C::YS + q) * YP + K + L.fx] = y;     // see MASKED below: outside columns stay zero
     }
     // ---- stage 4, row j - 3K: the new psi ----------------------------------------------------------------
     {

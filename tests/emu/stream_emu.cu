@@ -60,11 +60,18 @@ static int run(int rows, int cols, int grow0, int grows, int out_row0, int out_r
                     highest_waited = (it + 2 * C::K) / C::RB;
                     if (highest_waited >= g.nbatches) return 1;     // the kernel would wait for a batch never issued
                 }
+                // the kernel's choice of loop body, per block of U iterations: the domain masks only when one of the
+                // block's rows j - 3K .. j lies outside the domain (stream_2d.cu)
+                const int j0 = g.jstart + it / C::U * C::U;
+                const bool masked = j0 - C::SKEW < lane[0].dlo || j0 + C::U > lane[0].dlo + lane[0].dspan;
                 for (int t = 0; t < nact; ++t) {
                     const int half = (it / C::U) & 1;
-                    march_iter<C>(st[t], lane[t], g, c, wx, wy, it, it % C::U, ring + half * C::U * C::T + t,
-                                  ring + (half ^ 1) * C::U * C::T + t, pring.data() + half * C::U * C::T + t,
-                                  pring.data() + (half ^ 1) * C::U * C::T + t);
+                    const double2 *rh = ring + half * C::U * C::T + t, *ro = ring + (half ^ 1) * C::U * C::T + t;
+                    const double *ph = pring.data() + half * C::U * C::T + t, *po = pring.data() + (half ^ 1) * C::U * C::T + t;
+                    if (masked)
+                        march_iter<C, false, true>(st[t], lane[t], g, c, wx, wy, it, it % C::U, rh, ro, ph, po);
+                    else
+                        march_iter<C, false, false>(st[t], lane[t], g, c, wx, wy, it, it % C::U, rh, ro, ph, po);
                 }
                 if ((it + C::K + 1) % C::RB == 0) {
                     const int nb = (it + C::K + 1) / C::RB - 1 + C::NB;
