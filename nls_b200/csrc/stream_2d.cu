@@ -454,8 +454,10 @@ int launch_stream_sync(const Fused2DStep &s, const CrossWeights &w, const Stream
 template <typename C>
 int launch_stream_cfg(const Fused2DStep &s, const CrossWeights &w, const StreamPlan &p, cudaStream_t stream)
 {
-    if (s.peer) {           // the exchange-carrying step of a slab's cycle: shared coefficients, a single flavour
+    if (s.peer) {           // the exchange-carrying step of a slab's cycle: shared coefficients
         if (!s.uniform || s.diag_partial || s.batch != 1) return fail(NLSB_EINVAL, "the exchange-carrying step takes one grid with shared coefficients");
+        // same barrier cadence as the plain steps of the cycle
+        if (p.sync == kSyncPair) return launch_stream_sync<C, true, kSyncPair, false, true>(s, w, p, stream);
         return launch_stream_sync<C, true, kSyncEvery, false, true>(s, w, p, stream);
     }
     if (s.diag_partial)     // the diagnostics-carrying step of a chunk (one launch in many): a single flavour
