@@ -88,8 +88,10 @@ int nlsb_make_laplacian_2d_o7(int n, double h, double *blocks, int *orders);
 /* nls.f90:530-541  rgbmv(x, u, sign, op, klu, n):  u := u + sign * A x,  A banded (2klu+1, n) */
 int nlsb_rgbmv(const double *x, double *u, double sign, const double *op, int klu, int n);
 /* nls.f90:408-527  rbbmv[_o3|_o5|_o7](x, y, sign, blocks, ms, [m,] n):  y := y + sign * A x on n*n.
- * The block operator must be line-independent along the second index (it always is when built by
- * make_laplacian_2d); anything else fails with NLSB_EOPERATOR. */
+ * Any blocks memory of the make_laplacian_2d layout (ms = (0, .., k, .., 0)) is accepted, here and in
+ * hamiltonian_2d / runge_kutta_2d: constant-weight cross stencils (what make_laplacian_2d builds) take the fast
+ * kernels, weights that vary along the line take general kernels that read the blocks memory on the device.
+ * Other `ms` (which the reference's hard-wired block offsets cannot address either) fail with NLSB_EOPERATOR. */
 int nlsb_rbbmv(const double *x, double *y, double sign, const double *blocks, const int *ms, int m, int n);
 int nlsb_rbbmv_o3(const double *x, double *y, double sign, const double *blocks, const int *ms, int n);
 int nlsb_rbbmv_o5(const double *x, double *y, double sign, const double *blocks, const int *ms, int n);

@@ -615,6 +615,70 @@ int host_hamiltonian_2d(const CrossWeights &w, int n, int order, const double *p
     return 0;
 }
 
+// ---- general block-band operators (blocks memory that is not a constant-weight cross stencil) ---------------------
+// The fast kernels take (wx, wy); blocks_to_weights refuses everything else with NLSB_EOPERATOR.  When the blocks
+// memory still has the make_laplacian_2d LAYOUT (orders = (0, .., k, .., 0): the only layout rbbmv's hard-wired block
+// offsets can address, nls.f90:421-507) the entry points fall back to the general kernels of kernels_2d.cu.
+bool standard_block_orders(int m, const int *orders)
+{
+    if (m != 3 && m != 5 && m != 7) return false;
+    for (int b = 0; b < m; ++b)
+        if (orders[b] != (b == (m - 1) / 2 ? (m - 1) / 2 : 0)) return false;
+    return true;
+}
+
+int host_general_hamiltonian_2d(const double *blocks, int n, int m, const double *pumping, const double *coeffs,
+                                const double *u, double *v)
+{
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    const size_t np = (size_t)n * n;
+    double *d_b, *d_p, *d_c;
+    double2 *d_u, *d_v;
+    NLSB_TRY(mem.upload(&d_b, blocks, (size_t)n * (2 * m - 1)));
+    NLSB_TRY(mem.upload(&d_p, pumping, np));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.upload(&d_u, reinterpret_cast<const double2 *>(u), np));
+    NLSB_TRY(mem.alloc(&d_v, np));
+    Stage2DArgs a{1, n, n, d_u, d_u, d_p, d_c, nullptr, d_v, 0.0, 0.0, 0.0};
+    NLSB_TRY(launch_stage_2d_general(n, m, d_b, kStageRhs, a, s));
+    NLSB_CUDA(cudaMemcpyAsync(v, d_v, sizeof(double2) * np, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int host_general_rk4_2d(double dt, const double *blocks, int n, int m, int iters, const double *pumping,
+                        const double *coeffs, const double *u0, double *u)
+{
+    cudaStream_t s;
+    NLSB_TRY(internal_stream(&s));
+    Arena mem(s);
+    const size_t np = (size_t)n * n;
+    double *d_b, *d_p, *d_c;
+    double2 *d_psi, *d_work;
+    NLSB_TRY(mem.upload(&d_b, blocks, (size_t)n * (2 * m - 1)));
+    NLSB_TRY(mem.upload(&d_p, pumping, np));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.upload(&d_psi, reinterpret_cast<const double2 *>(u0), np));
+    NLSB_TRY(mem.alloc(&d_work, 3 * np));
+    double2 *ya = d_work, *yb = d_work + np, *acc = d_work + 2 * np;
+    Stage2DArgs a{1, n, n, nullptr, d_psi, d_p, d_c, acc, nullptr, 0.0, 1.0, dt / 6};
+    for (int it = 0; it < iters; ++it) {      // runge_kutta_2d, nls.f90:892-899: four right-hand sides per step
+        a.ysrc = d_psi; a.ydst = ya; a.cy = dt / 2;
+        NLSB_TRY(launch_stage_2d_general(n, m, d_b, kStageFirst, a, s));
+        a.ysrc = ya; a.ydst = yb; a.cy = dt / 2;
+        NLSB_TRY(launch_stage_2d_general(n, m, d_b, kStageMid, a, s));
+        a.ysrc = yb; a.ydst = ya; a.cy = dt;
+        NLSB_TRY(launch_stage_2d_general(n, m, d_b, kStageMid, a, s));
+        a.ysrc = ya; a.ydst = d_psi; a.cy = 0.0;
+        NLSB_TRY(launch_stage_2d_general(n, m, d_b, kStageLast, a, s));
+    }
+    NLSB_CUDA(cudaMemcpyAsync(u, d_psi, sizeof(double2) * np, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 // mu = i*E'/M from the four sums {Re M, Im M, Re E', Im E'} (nls.f90:946-947, :968-970)
 void chemical_potential_from_dots(const double d[4], double mu[2])
 {
@@ -783,7 +847,8 @@ int nlsb_rbbmv(const double *x, double *y, double sign, const double *blocks, co
 {
     if (!x || !y || !blocks || !ms || n < 1) return fail(NLSB_EINVAL, "rbbmv: bad arguments");
     CrossWeights w{};
-    NLSB_TRY(blocks_to_weights(n, m, blocks, ms, w.wx, w.wy));
+    const int cross = blocks_to_weights(n, m, blocks, ms, w.wx, w.wy);
+    if (cross && !(cross == NLSB_EOPERATOR && standard_block_orders(m, ms) && n >= m)) return cross;
     cudaStream_t s;
     NLSB_TRY(internal_stream(&s));
     Arena mem(s);
@@ -791,7 +856,13 @@ int nlsb_rbbmv(const double *x, double *y, double sign, const double *blocks, co
     double *d_x, *d_y;
     NLSB_TRY(mem.upload(&d_x, x, np));
     NLSB_TRY(mem.upload(&d_y, y, np));
-    NLSB_TRY(launch_cross_matvec_2d(n, n, m, w, d_x, d_y, sign, s));
+    if (cross) {       // weights that vary along the line: the general kernel, reading the blocks memory itself
+        double *d_b;
+        NLSB_TRY(mem.upload(&d_b, blocks, (size_t)n * (2 * m - 1)));
+        NLSB_TRY(launch_general_matvec_2d(n, m, d_b, d_x, d_y, sign, s));
+    } else {
+        NLSB_TRY(launch_cross_matvec_2d(n, n, m, w, d_x, d_y, sign, s));
+    }
     NLSB_CUDA(cudaMemcpyAsync(y, d_y, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
     NLSB_CUDA(cudaStreamSynchronize(s));
     return 0;
@@ -848,7 +919,10 @@ int nlsb_hamiltonian_2d(const double *pumping, const double *coeffs, const doubl
     NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     CrossWeights w{};
-    NLSB_TRY(blocks_to_weights(n, order, blocks, orders, w.wx, w.wy));
+    const int cross = blocks_to_weights(n, order, blocks, orders, w.wx, w.wy);
+    if (cross == NLSB_EOPERATOR && standard_block_orders(order, orders))
+        return host_general_hamiltonian_2d(blocks, n, order, pumping, coeffs, u, v);
+    if (cross) return cross;
     return host_hamiltonian_2d(w, n, order, pumping, coeffs, u, v, nullptr);
 }
 
@@ -873,7 +947,10 @@ int nlsb_runge_kutta_2d(double dt, double t0, const double *u0, int n, const dou
     NLSB_TRY(check_coeffs(coeffs));
     NLSB_TRY(check_order_size(n, order));
     CrossWeights w{};
-    NLSB_TRY(blocks_to_weights(n, order, blocks, orders, w.wx, w.wy));
+    const int cross = blocks_to_weights(n, order, blocks, orders, w.wx, w.wy);
+    if (cross == NLSB_EOPERATOR && standard_block_orders(order, orders))
+        return host_general_rk4_2d(dt, blocks, n, order, iters, pumping, coeffs, u0, u);
+    if (cross) return cross;
     return host_rk4_2d(dt, w, n, order, iters, pumping, coeffs, u0, u);
 }
 

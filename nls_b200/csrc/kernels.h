@@ -40,6 +40,11 @@ struct Stage2DArgs {
     double dt6;             // dt/6
 };
 int launch_stage_2d(int order, StageMode mode, const CrossWeights &w, const Stage2DArgs &a, cudaStream_t stream);
+// General block-band operator (any blocks memory of the make_laplacian_2d layout, m = 3 / 5 / 7; kernels_2d.cu):
+// blocks_dev is the device copy of the blocks memory; arrays in the reference's memory order (line = slow index).
+int launch_stage_2d_general(int n, int m, const double *blocks_dev, StageMode mode, const Stage2DArgs &a, cudaStream_t stream);
+int launch_general_matvec_2d(int n, int m, const double *blocks_dev, const double *x, double *y, double sign,
+                             cudaStream_t stream);
 // The halo exchange a slab's step launch performs itself (strip-marching kernel, multi-GPU; peer.cu / stream_2d.cu):
 // new psi rows [up_row0, up_row0 + nrows) also go to (address of the local store + up_delta bytes) = the halo rows of
 // the rank above, rows [dn_row0, dn_row0 + nrows) to the rank below; flags as in peer_flags.cuh (null: no neighbour).

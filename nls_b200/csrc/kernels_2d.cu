@@ -104,6 +104,100 @@ cross_matvec_2d_kernel(int rows, int cols, WeightsK<K> w, const double *__restri
     yio[g] = fma(sign, s, yio[g]);
 }
 
+// ---- general block-band operator ---------------------------------------------------------------------------------
+// rbbmv (nls.f90:408-527) accepts ANY blocks memory of the make_laplacian_2d layout: m - 1 off-diagonal blocks that
+// are diagonals of n entries (weight of line i + s at position p: blk_b[p], s = b - k) and a middle block that is an
+// m x n band along the line (A(p, q) = band(k + p - q, q), BLAS GB storage).  The fast kernels take the constant-weight
+// cross stencil only (blocks_to_weights); an operator whose entries vary along the line -- variable coefficients,
+// anisotropy, a user's own boundary rows -- runs through the kernels below: same right-hand side and stage algebra,
+// the weights read from the blocks memory on the device.  One node per thread, no tiling: a compatibility path.
+//
+// Orientation: `line` is the index rbbmv cuts the flattened vector by, `pos` the index inside a line; element
+// (line, pos) sits at line * n + pos.  The (n, n) arrays of hamiltonian_2d / runge_kutta_2d arrive at the C ABI in the
+// reference's (Fortran) memory order, whose lines are the slow index as well (nls_b200/native.py hands them over so).
+struct GeneralOp {
+    const double *blocks;    // device copy of the blocks memory, n (2m - 1) doubles
+    int m, n;
+};
+
+__device__ __forceinline__ const double *general_block(const GeneralOp &op, int b)
+{
+    const int k = (op.m - 1) / 2;
+    const size_t n = (size_t)op.n;
+    return op.blocks + (b <= k ? (size_t)b * n : (size_t)k * n + (size_t)op.m * n + (size_t)(b - k - 1) * n);
+}
+
+template <typename T, typename Load>
+__device__ __forceinline__ void general_apply(const GeneralOp &op, int line, int pos, Load load, T &acc)
+{
+    const int k = (op.m - 1) / 2, n = op.n;
+    for (int b = 0; b < op.m; ++b) {
+        if (b == k) {
+            const double *band = general_block(op, k);
+            const int lo = pos - k > 0 ? pos - k : 0, hi = pos + k < n - 1 ? pos + k : n - 1;
+            for (int q = lo; q <= hi; ++q) acc.add(band[(size_t)(k + pos - q) + (size_t)op.m * q], load(line, q));
+        } else {
+            const int src = line + (b - k);
+            if (src >= 0 && src < n) acc.add(general_block(op, b)[pos], load(src, pos));
+        }
+    }
+}
+
+struct RealAcc {
+    double s = 0.0;
+    __device__ __forceinline__ void add(double w, double v) { s = fma(w, v, s); }
+};
+struct ComplexAcc {
+    double re = 0.0, im = 0.0;
+    __device__ __forceinline__ void add(double w, double2 v)
+    {
+        re = fma(w, v.x, re);
+        im = fma(w, v.y, im);
+    }
+};
+
+__global__ void __launch_bounds__(256)
+general_matvec_2d_kernel(GeneralOp op, const double *__restrict__ xin, double *__restrict__ yio, double sign)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, bidx = blockIdx.y * blockDim.y + threadIdx.y;
+    if (a >= op.n || bidx >= op.n) return;
+    const size_t g = (size_t)bidx * op.n + a;                    // memory order: a (= pos) is the contiguous index
+    const int line = bidx, pos = a;
+    RealAcc acc;
+    general_apply(op, line, pos, [&](int l, int p) { return xin[(size_t)l * op.n + p]; }, acc);
+    yio[g] = fma(sign, acc.s, yio[g]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+stage_2d_general_kernel(GeneralOp op, const double2 *__restrict__ ysrc, const double2 *__restrict__ ubase,
+                        const double *__restrict__ pumping, const double *__restrict__ coeffs, double2 *__restrict__ acc,
+                        double2 *__restrict__ ydst, double cy, double dt6)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, bidx = blockIdx.y * blockDim.y + threadIdx.y;
+    if (a >= op.n || bidx >= op.n) return;
+    const size_t g = (size_t)bidx * op.n + a;
+    const int line = bidx, pos = a;
+    const RhsCoeffs c = load_rhs_coeffs(coeffs);
+    ComplexAcc lap;
+    general_apply(op, line, pos, [&](int l, int p) { return ysrc[(size_t)l * op.n + p]; }, lap);
+    const double2 centre = ysrc[g];
+    const double2 k = rhs_point(c, c.c12 * pumping[g], centre, lap.re, lap.im);
+    if (MODE == kStageRhs) {
+        ydst[g] = k;
+    } else if (MODE == kStageFirst) {
+        acc[g] = k;
+        ydst[g] = make_double2(fma(k.x, cy, centre.x), fma(k.y, cy, centre.y));
+    } else if (MODE == kStageMid) {
+        const double2 u = ubase[g], s = acc[g];
+        acc[g] = make_double2(fma(2.0, k.x, s.x), fma(2.0, k.y, s.y));
+        ydst[g] = make_double2(fma(k.x, cy, u.x), fma(k.y, cy, u.y));
+    } else {
+        const double2 u = ubase[g], s = acc[g];
+        ydst[g] = make_double2(fma(s.x + k.x, dt6, u.x), fma(s.y + k.y, dt6, u.y));
+    }
+}
+
 __global__ void reservoir_kernel(size_t npts, RhsCoeffs c, const double *__restrict__ pumping,
                                  const double *__restrict__ u_sqr, double *__restrict__ r)
 {
@@ -155,6 +249,33 @@ int launch_stage_2d(int order, StageMode mode, const CrossWeights &w, const Stag
     case 7: return launch_stage_k<3>(mode, w, a, stream);
     }
     return fail(NLSB_EORDER, "order must be 3, 5 or 7 (got %d)", order);
+}
+
+int launch_general_matvec_2d(int n, int m, const double *blocks_dev, const double *x, double *y, double sign,
+                             cudaStream_t stream)
+{
+    const dim3 block(64, 4), grid((n + block.x - 1) / block.x, (n + block.y - 1) / block.y);
+    general_matvec_2d_kernel<<<grid, block, 0, stream>>>(GeneralOp{blocks_dev, m, n}, x, y, sign);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int launch_stage_2d_general(int n, int m, const double *blocks_dev, StageMode mode, const Stage2DArgs &a, cudaStream_t stream)
+{
+    if (a.batch != 1 || a.rows != n || a.cols != n) return fail(NLSB_EINVAL, "general operator: one n x n grid");
+    const dim3 block(64, 4), grid((n + block.x - 1) / block.x, (n + block.y - 1) / block.y);
+    const GeneralOp op{blocks_dev, m, n};
+#define NLSB_LAUNCH_GENERAL(MODE) \
+    stage_2d_general_kernel<MODE><<<grid, block, 0, stream>>>(op, a.ysrc, a.ubase, a.pumping, a.coeffs, a.acc, a.ydst, a.cy, a.dt6)
+    switch (mode) {
+    case kStageRhs: NLSB_LAUNCH_GENERAL(kStageRhs); break;
+    case kStageFirst: NLSB_LAUNCH_GENERAL(kStageFirst); break;
+    case kStageMid: NLSB_LAUNCH_GENERAL(kStageMid); break;
+    case kStageLast: NLSB_LAUNCH_GENERAL(kStageLast); break;
+    }
+#undef NLSB_LAUNCH_GENERAL
+    count_launches(1);
+    return (int)cudaGetLastError();
 }
 
 int launch_cross_matvec_2d(int rows, int cols, int order, const CrossWeights &w, const double *x, double *y,

@@ -74,6 +74,35 @@ def test_rbbmv(nls, order):
     assert np.abs(y - want).max() <= 1e-13 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("order", [3, 5, 7])
+def test_general_block_band_operators(nls, order):
+    """rbbmv / hamiltonian_2d / runge_kutta_2d accept ANY blocks memory of the make_laplacian_2d layout
+    (nls.f90:408-527): weights that vary along the line -- every entry of the reference's operator scaled by its own
+    random factor here -- take the general kernels (kernels_2d.cu) instead of being refused; both orientations (flat
+    vectors of rbbmv: line-major; (n, n) arrays: the reference's lines are Fortran columns) against the oracle."""
+    n = 29
+    rng = np.random.default_rng(40 + order)
+    blocks, orders = O.dp.make_laplacian_2d(n, order, 0.2)
+    blocks = np.asfortranarray(blocks * (0.5 + rng.random(blocks.shape)))
+    wx, wy = np.zeros(7), np.zeros(7)
+    from nls_b200 import _lib
+    import ctypes as C
+    assert _lib.load().nlsb_blocks_to_weights(n, order, blocks.ctypes.data_as(C.c_void_p), orders.ctypes.data_as(C.c_void_p),
+                                              wx.ctypes.data_as(C.c_void_p), wy.ctypes.data_as(C.c_void_p)) == -5
+    x, y = rng.standard_normal(n * n), rng.standard_normal(n * n)
+    want = O.dp.rbbmv(x, y, -1.0, blocks, orders, n)
+    nls.rbbmv(x, y, -1.0, blocks, orders, n)
+    assert np.abs(y - want).max() <= 1e-13 * np.abs(want).max()
+    m = model_2d(n, order=order, radius=0.8)
+    c, P = m.getCoefficients(), m.getPumping() * (0.5 + rng.random((n, n)))
+    u = rough_field((n, n), order) * 0.3 + 0.2 + 0.1j * rng.standard_normal((n, n))       # no symmetry at all
+    assert rel_l2(nls.hamiltonian_2d(P, c, u, blocks, orders), O.dp.hamiltonian_2d(P, c, u, blocks, orders)) <= 1e-13
+    got = nls.runge_kutta_2d(1e-4, 0.0, u, blocks, orders, 7, P, c)
+    assert rel_l2(got, O.dp.runge_kutta_2d(1e-4, 0.0, u, blocks, orders, 7, P, c)) <= 1e-12
+    # a transposed field must NOT give the transposed result: the operator is no longer symmetric under x <-> y
+    assert rel_l2(nls.hamiltonian_2d(P.T, c, u.T, blocks, orders).T, nls.hamiltonian_2d(P, c, u, blocks, orders)) > 1e-6
+
+
 def test_revervoir(nls):
     rng = np.random.default_rng(5)
     c = model_1d(16).getCoefficients()
