@@ -259,6 +259,61 @@ std::mutex g_graph_mutex;
 LoopGraph g_graphs[8] = {};
 unsigned long long g_graph_stamp = 0;
 
+LoopKey make_loop_key(const void *psi, const void *work, const void *pumping, const void *coeffs, int batch, int rows,
+                      int cols, int order, int path, double dt, const CrossWeights &w, int *rc)
+{
+    LoopKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.psi = psi; key.work = work; key.pumping = pumping; key.coeffs = coeffs;
+    key.batch = batch; key.rows = rows; key.cols = cols; key.order = order; key.path = path;
+    cudaError_t e = cudaGetDevice(&key.device);
+    *rc = e == cudaSuccess ? 0 : cuda_fail(e, "cudaGetDevice");
+    key.has_uniform = g_uniform_coeffs ? 1 : 0;
+    if (g_uniform_coeffs) key.uniform = *g_uniform_coeffs;
+    stream_2d_get_tuning(key.tune);
+    key.dt = dt;
+    key.w = w;
+    return key;
+}
+
+// The cached executable graph of `key`, recorded by `record(stream, &rc)` (a chunk of step launches) on first use.
+// Call with g_graph_mutex held; the returned slot stays valid while the mutex is held.
+template <class Record>
+int cached_loop_graph(const LoopKey &key, int launches_recorded, Record record, cudaGraphExec_t *exec_out)
+{
+    LoopGraph *slot = nullptr, *victim = &g_graphs[0];
+    for (LoopGraph &g : g_graphs) {
+        if (g.exec && std::memcmp(&g.key, &key, sizeof(key)) == 0) slot = &g;
+        if (!g.exec || (victim->exec && g.stamp < victim->stamp)) victim = &g;
+    }
+    if (!slot) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t rec;
+        NLSB_TRY(internal_stream(&rec));
+        NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        record(rec, &rc);
+        cudaError_t e = cudaStreamEndCapture(rec, &graph);
+        count_launches(0ull - (unsigned long long)launches_recorded);   // recorded, not run
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+        if (victim->exec) cudaGraphExecDestroy(victim->exec);   // released once its in-flight launches complete
+        victim->key = key;
+        victim->exec = exec;
+        slot = victim;
+    }
+    slot->stamp = ++g_graph_stamp;
+    *exec_out = slot->exec;
+    return 0;
+}
+
 int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, double dt, const CrossWeights &w,
                          const double *pumping, const double *coeffs, double2 *psi, double2 *work, cudaStream_t stream,
                          const DiagRequest *diag = nullptr)
@@ -285,47 +340,16 @@ int enqueue_rk4_2d_fused(int batch, int rows, int cols, int order, int iters, do
         }
     }
     if (cap == cudaStreamCaptureStatusNone && replayable >= 2 * chunk) {
-        LoopKey key;
-        std::memset(&key, 0, sizeof(key));
-        key.psi = psi; key.work = work; key.pumping = pumping; key.coeffs = coeffs;
-        key.batch = batch; key.rows = rows; key.cols = cols; key.order = order; key.path = g_path_2d.load();
-        NLSB_CUDA(cudaGetDevice(&key.device));
-        key.has_uniform = g_uniform_coeffs ? 1 : 0;
-        if (g_uniform_coeffs) key.uniform = *g_uniform_coeffs;
-        stream_2d_get_tuning(key.tune);
-        key.dt = dt;
-        key.w = w;
+        int krc = 0;
+        const LoopKey key = make_loop_key(psi, work, pumping, coeffs, batch, rows, cols, order, g_path_2d.load(), dt, w, &krc);
+        if (krc) return krc;
         std::lock_guard<std::mutex> lock(g_graph_mutex);
-        LoopGraph *slot = nullptr, *victim = &g_graphs[0];
-        for (LoopGraph &g : g_graphs) {
-            if (g.exec && std::memcmp(&g.key, &key, sizeof(key)) == 0) slot = &g;
-            if (!g.exec || (victim->exec && g.stamp < victim->stamp)) victim = &g;
-        }
-        if (!slot) {
-            cudaGraph_t graph = nullptr;
-            cudaGraphExec_t exec = nullptr;
-            cudaStream_t rec;
-            NLSB_TRY(internal_stream(&rec));
-            NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
-            enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, &rc, nullptr, p_pitch);
-            cudaError_t e = cudaStreamEndCapture(rec, &graph);
-            count_launches(0ull - (unsigned long long)chunk);
-            if (rc) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc;
-            }
-            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
-            e = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
-            if (victim->exec) cudaGraphExecDestroy(victim->exec);   // released once its in-flight launches complete
-            victim->key = key;
-            victim->exec = exec;
-            slot = victim;
-        }
-        slot->stamp = ++g_graph_stamp;
+        cudaGraphExec_t exec = nullptr;
+        NLSB_TRY(cached_loop_graph(key, chunk, [&](cudaStream_t rec, int *r) {
+            enqueue_fused_steps_2d(batch, rows, cols, order, dt, w, pumping, coeffs, psi, work, 0, chunk, rec, r, nullptr, p_pitch);
+        }, &exec));
         for (; done + chunk <= replayable; done += chunk) {
-            cudaError_t e = cudaGraphLaunch(slot->exec, stream);
+            cudaError_t e = cudaGraphLaunch(exec, stream);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
             count_launches((unsigned long long)chunk);
         }
@@ -383,29 +407,20 @@ int enqueue_rk4_2d_planar(int batch, int rows, int cols, int order, int iters, d
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     NLSB_CUDA(cudaStreamIsCapturing(stream, &cap));
     if (cap == cudaStreamCaptureStatusNone && iters >= 2 * chunk) {
-        cudaGraph_t graph = nullptr;
+        // the chunk's launches depend on the planar working copy inside `work` (tensor maps by value), the geometry and
+        // the coefficients: repeated calls on the same buffers replay the cached executable (capture + instantiation
+        // cost about a millisecond per call -- 3 % of a 5000-step solve of the 512^2 grid)
+        int krc = 0;
+        const LoopKey key = make_loop_key(psi, work, pumping, coeffs, batch, rows, cols, order, 100 + variant, dt, w, &krc);
+        if (krc) return krc;
+        std::lock_guard<std::mutex> lock(g_graph_mutex);
         cudaGraphExec_t exec = nullptr;
-        cudaStream_t rec;
-        NLSB_TRY(internal_stream(&rec));
-        NLSB_CUDA(cudaStreamBeginCapture(rec, cudaStreamCaptureModeThreadLocal));
-        steps(0, chunk, rec, &rc);
-        cudaError_t e = cudaStreamEndCapture(rec, &graph);
-        count_launches(0ull - (unsigned long long)chunk);
-        if (rc) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
-        }
-        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
-        e = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+        NLSB_TRY(cached_loop_graph(key, chunk, [&](cudaStream_t rec, int *r) { steps(0, chunk, rec, r); }, &exec));
         for (; done + chunk <= iters; done += chunk) {
-            e = cudaGraphLaunch(exec, stream);
-            if (e != cudaSuccess) break;
+            cudaError_t e = cudaGraphLaunch(exec, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
             count_launches((unsigned long long)chunk);
         }
-        cudaGraphExecDestroy(exec);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
     }
     steps(done, iters - done, stream, &rc);
     if (rc) return rc;
