@@ -247,6 +247,34 @@ def test_stream_kernel_is_bitwise_equal_to_tile_kernel(nls, order, n, iters):
     assert rel_l2(a, O.dp.solve_nls_2d(*args)) <= 1e-10
 
 
+def test_stream_kernel_random_geometries_are_bitwise_equal_to_tile_kernel(nls):
+    """Random grid sizes x strip widths x rows per CTA x barrier cadence (nlsb_set_stream_tuning): last strips of one
+    to eight warps, single-chunk and many-chunk strips, grids narrower than one strip -- always the tile kernel's bits."""
+    from nls_b200 import _lib
+    from nls_b200.engine import set_2d_path
+    rng = np.random.default_rng(2024)
+    try:
+        for case in range(14):
+            order = int(rng.choice([3, 5, 5, 5, 7]))
+            n = int(rng.integers(order, 620))
+            width = int(rng.choice([0, 128, 256])) if order != 7 else 0
+            rows_per_cta = int(rng.choice([0, 0, 40, 90]))
+            sync = int(rng.choice([-1, 0, 1]))
+            m = model_2d(n, 3, order=order, radius=min(10.0, n * 0.1 / 4))
+            P = m.getPumping() * (1.0 + 0.5 * rng.random((n, n)))
+            args = (m.dt, m.dx, order, 3, P, m.getCoefficients(), rough_field((n, n), case) * 0.05 + 0.1)
+            set_2d_path("fused32")
+            want = nls.solve_nls_2d(*args)
+            set_2d_path("stream")
+            _lib.call("nlsb_set_stream_tuning", sync, width, rows_per_cta)
+            got = nls.solve_nls_2d(*args)
+            _lib.call("nlsb_set_stream_tuning", -1, 0, 0)
+            assert np.array_equal(got, want), (case, order, n, width, rows_per_cta, sync)
+    finally:
+        _lib.call("nlsb_set_stream_tuning", -1, 0, 0)
+        set_2d_path("auto")
+
+
 @pytest.mark.parametrize("order,n,iters", [(5, 512, 40), (3, 300, 30)])
 def test_resident_kernel_is_bitwise_equal_to_tile_kernel(nls, order, n, iters):
     """The register-resident kernel (one patch per CTA, edge nodes exchanged through L2 mailboxes every RK stage)
