@@ -555,9 +555,119 @@ int host_rk4_1d(double dt, const double *taps_host, int n, int order, int iters,
     return 0;
 }
 
+// ---- host-buffer solve of a LARGE grid with the transfers overlapped ---------------------------------------------
+// A solve from host buffers is H2D (24 B per node) + iters steps + D2H (16 B per node); on 8192^2 with 200 steps the
+// copies are 48 of 248 ms.  A node's arithmetic does not depend on the launch that computes it (the property the slab
+// decomposition rests on), so the grid can be advanced in two row ranges that run AHEAD of each other:
+//   start  the top rows [0, R + 4k s) are uploaded first and take s steps while the bottom rows are still on the bus
+//          -- step j on rows [0, R + 4k (s - j)): every step loses the 4k rows whose neighbours are not there yet --
+//          then the bottom range catches up, step j on the complementary rows [R + 4k (s - j), n);
+//   end    the top range runs s' steps ahead again (step j on [0, R + 4k (s' - j))), its rows [0, R) leave for the host
+//          while the bottom range takes its last s' steps.
+// Both ranges ping-pong between the same two buffers; a range's step j never overwrites rows the other range's step j
+// still reads (they lie 4k rows beyond its edge).  Bit-identical to the plain loop; s, s' are even so that the middle
+// part starts and ends in `psi`.  With pageable host memory the copies do not overlap anything (cudaMemcpyAsync stages
+// them synchronously) and the scheme costs the 4k s redundant rows of the catch-up ranges' neighbours only.
+int copy_stream(cudaStream_t *out)
+{
+    static thread_local cudaStream_t streams[64] = {};
+    int dev = 0;
+    NLSB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(NLSB_EINVAL, "device ordinal %d out of range", dev);
+    if (!streams[dev]) NLSB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    *out = streams[dev];
+    return 0;
+}
+
+struct ScopedEvent {
+    cudaEvent_t ev = nullptr;
+    int create()
+    {
+        NLSB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        return 0;
+    }
+    ~ScopedEvent()
+    {
+        if (ev) cudaEventDestroy(ev);
+    }
+};
+
+bool pipelined_solve_applies(int n, int order, int iters)
+{
+    const int path = g_path_2d.load();
+    if (path != 0 && path != 8) return false;
+    const int halo = 2 * (order - 1);          // 4k rows per step
+    // both row ranges must be grids the strip-marching kernel takes (>= 2^20 nodes, even column count) and the
+    // head start must stay a small part of the range
+    return (n & 1) == 0 && (long long)(n / 2) * n >= (1ll << 21) && iters >= 160 && 28 * halo <= n / 8;
+}
+
+int host_rk4_2d_pipelined(double dt, const CrossWeights &w, int n, int order, int iters, const double *pumping,
+                          const double *coeffs, const double *u0, double *u)
+{
+    cudaStream_t s, c;
+    NLSB_TRY(internal_stream(&s));
+    NLSB_TRY(copy_stream(&c));
+    Arena mem(s);
+    struct DrainOnExit {     // declared after the arena: an early return must not free buffers the copy stream still uses
+        cudaStream_t st;
+        ~DrainOnExit() { cudaStreamSynchronize(st); }
+    } drain{c};
+    const size_t np = (size_t)n * n, row = (size_t)n;
+    const int halo = 2 * (order - 1);
+    // head starts: the steps a half grid takes while the other half's bytes cross the bus (24 B in, 16 B out per node
+    // against about 1.4e-11 s per node-step on B200: 28 and 20 steps at 50 GB/s), even
+    const int s_up = 28, s_dn = 20;
+    const int R = n / 2, R_up = R + halo * s_up;
+    double *d_p, *d_c;
+    double2 *d_psi, *d_work;
+    NLSB_TRY(mem.alloc(&d_p, np));
+    NLSB_TRY(mem.upload(&d_c, coeffs, (size_t)23));
+    NLSB_TRY(mem.alloc(&d_psi, np));
+    NLSB_TRY(mem.alloc(&d_work, nlsb_dev_rk4_2d_workspace(1, n, n) / sizeof(double2) + 1));
+    ScopedEvent ready, top_in, bot_in, top_out;
+    NLSB_TRY(ready.create()); NLSB_TRY(top_in.create()); NLSB_TRY(bot_in.create()); NLSB_TRY(top_out.create());
+    NLSB_CUDA(cudaEventRecord(ready.ev, s));                   // the allocations are ordered on s
+    NLSB_CUDA(cudaStreamWaitEvent(c, ready.ev, 0));
+    const double2 *h_u0 = reinterpret_cast<const double2 *>(u0);
+    NLSB_CUDA(cudaMemcpyAsync(d_p, pumping, sizeof(double) * R_up * row, cudaMemcpyHostToDevice, c));
+    NLSB_CUDA(cudaMemcpyAsync(d_psi, h_u0, sizeof(double2) * R_up * row, cudaMemcpyHostToDevice, c));
+    NLSB_CUDA(cudaEventRecord(top_in.ev, c));
+    NLSB_CUDA(cudaMemcpyAsync(d_p + R_up * row, pumping + R_up * row, sizeof(double) * (n - R_up) * row, cudaMemcpyHostToDevice, c));
+    NLSB_CUDA(cudaMemcpyAsync(d_psi + R_up * row, h_u0 + R_up * row, sizeof(double2) * (n - R_up) * row, cudaMemcpyHostToDevice, c));
+    NLSB_CUDA(cudaEventRecord(bot_in.ev, c));
+
+    UniformCoeffsScope uniform(coeffs);
+    Fused2DStep st{1, n, n, 0, n, 0, n, nullptr, nullptr, d_p, d_c, dt, g_uniform_coeffs};
+    auto range_step = [&](int j, int row0, int row1) {          // step j (1-based within its phase): buffer parity j
+        st.in = (j & 1) ? d_psi : d_work;
+        st.out = (j & 1) ? d_work : d_psi;
+        st.out_row0 = row0;
+        st.out_row1 = row1;
+        return launch_interleaved_step(order, st, w, s);
+    };
+    NLSB_CUDA(cudaStreamWaitEvent(s, top_in.ev, 0));
+    for (int j = 1; j <= s_up; ++j) NLSB_TRY(range_step(j, 0, R + halo * (s_up - j)));
+    NLSB_CUDA(cudaStreamWaitEvent(s, bot_in.ev, 0));
+    for (int j = 1; j <= s_up; ++j) NLSB_TRY(range_step(j, R + halo * (s_up - j), n));
+    // middle: whole-grid steps (cached graphs), state in d_psi before and after
+    NLSB_TRY(enqueue_rk4_2d(1, n, n, order, iters - s_up - s_dn, dt, w, d_p, d_c, d_psi, d_work, s));
+    for (int j = 1; j <= s_dn; ++j) NLSB_TRY(range_step(j, 0, R + halo * (s_dn - j)));
+    NLSB_CUDA(cudaEventRecord(top_out.ev, s));
+    NLSB_CUDA(cudaStreamWaitEvent(c, top_out.ev, 0));
+    double2 *h_u = reinterpret_cast<double2 *>(u);
+    NLSB_CUDA(cudaMemcpyAsync(h_u, d_psi, sizeof(double2) * R * row, cudaMemcpyDeviceToHost, c));
+    for (int j = 1; j <= s_dn; ++j) NLSB_TRY(range_step(j, R + halo * (s_dn - j), n));
+    NLSB_CUDA(cudaMemcpyAsync(h_u + R * row, d_psi + R * row, sizeof(double2) * (n - R) * row, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaStreamSynchronize(c));
+    NLSB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int host_rk4_2d(double dt, const CrossWeights &w, int n, int order, int iters, const double *pumping,
                 const double *coeffs, const double *u0, double *u)
 {
+    if (pipelined_solve_applies(n, order, iters)) return host_rk4_2d_pipelined(dt, w, n, order, iters, pumping, coeffs, u0, u);
     cudaStream_t s;
     NLSB_TRY(internal_stream(&s));
     Arena mem(s);

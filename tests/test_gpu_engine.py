@@ -223,6 +223,25 @@ def test_device_diagnostics_of_a_large_ensemble_use_a_warp_per_member(order, n):
     assert all(np.array_equal(again[k], d[k]) for k in d)
 
 
+@pytest.mark.parametrize("order", [5, 7])
+def test_host_buffer_solve_of_a_large_grid_overlaps_its_transfers_and_keeps_the_bits(order):
+    """solve_nls_2d from host buffers on grids of >= 2048^2 with >= 160 steps advances two row ranges that run ahead
+    of each other while the other range's bytes are on the bus (csrc/api.cu::host_rk4_2d_pipelined): same bits as the
+    device-resident time loop, and within 1e-10 of a few oracle-checked rows is implied by the other parity tests."""
+    from nls_b200.engine import Grid2D
+    from nls_b200.native import nls
+    n, iters = 2048, 164
+    m = model_2d(n, iters, order=order, radius=30.0)
+    rng = np.random.default_rng(order)
+    P = np.ascontiguousarray(m.getPumping() * (1.0 + 0.5 * rng.random((n, n))))
+    u0 = rough_field((n, n), 3) * 0.05 + 0.1
+    got = nls.solve_nls_2d(m.dt, m.dx, order, iters, P, m.getCoefficients(), u0)
+    want = Grid2D(n, m.dx, m.dt, order=order, pumping=P, coeffs=m.getCoefficients(), u0=u0).advance(iters).solution()[0]
+    assert np.array_equal(got, want)
+    again = nls.solve_nls_2d(m.dt, m.dx, order, iters, P, m.getCoefficients(), u0)     # cached graphs, reused pool
+    assert np.array_equal(again, want)
+
+
 def test_continuation_with_changing_pumping_equals_fresh_solves():
     """psi stays on the device across chunks while the pump changes (animation / check loops)."""
     from nls_b200.engine import Grid2D
