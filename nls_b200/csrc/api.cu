@@ -559,11 +559,12 @@ int host_rk4_1d(double dt, const double *taps_host, int n, int order, int iters,
 // A solve from host buffers is H2D (24 B per node) + iters steps + D2H (16 B per node); on 8192^2 with 200 steps the
 // copies are 48 of 248 ms.  A node's arithmetic does not depend on the launch that computes it (the property the slab
 // decomposition rests on), so the grid can be advanced in two row ranges that run AHEAD of each other:
-//   start  the top rows [0, R + 4k s) are uploaded first and take s steps while the bottom rows are still on the bus
-//          -- step j on rows [0, R + 4k (s - j)): every step loses the 4k rows whose neighbours are not there yet --
-//          then the bottom range catches up, step j on the complementary rows [R + 4k (s - j), n);
-//   end    the top range runs s' steps ahead again (step j on [0, R + 4k (s' - j))), its rows [0, R) leave for the host
-//          while the bottom range takes its last s' steps.
+//   start  the top rows [0, R + 4k s) (R = a quarter to a half of the grid) are uploaded first and take s steps while the
+//          other rows are still on the bus -- step j on rows [0, R + 4k (s - j)): every step loses the 4k rows whose
+//          neighbours are not there yet -- then the bottom range catches up, step j on the complementary rows
+//          [R + 4k (s - j), n);
+//   end    the top range [0, R') (all but the last quarter to half) runs s' steps ahead again (step j on
+//          [0, R' + 4k (s' - j))) and leaves for the host while the bottom range takes its last s' steps.
 // Both ranges ping-pong between the same two buffers; a range's step j never overwrites rows the other range's step j
 // still reads (they lie 4k rows beyond its edge).  Bit-identical to the plain loop; s, s' are even so that the middle
 // part starts and ends in `psi`.  With pageable host memory the copies do not overlap anything (cudaMemcpyAsync stages
@@ -599,7 +600,7 @@ bool pipelined_solve_applies(int n, int order, int iters)
     const int halo = 2 * (order - 1);          // 4k rows per step
     // both row ranges must be grids the strip-marching kernel takes (>= 2^20 nodes, even column count) and the
     // head start must stay a small part of the range
-    return (n & 1) == 0 && (long long)(n / 2) * n >= (1ll << 21) && iters >= 160 && 28 * halo <= n / 8;
+    return (n & 1) == 0 && (long long)(n / 4) * n >= (1ll << 20) && iters >= 160 && 28 * halo <= n / 8;
 }
 
 int host_rk4_2d_pipelined(double dt, const CrossWeights &w, int n, int order, int iters, const double *pumping,
@@ -615,10 +616,23 @@ int host_rk4_2d_pipelined(double dt, const CrossWeights &w, int n, int order, in
     } drain{c};
     const size_t np = (size_t)n * n, row = (size_t)n;
     const int halo = 2 * (order - 1);
-    // head starts: the steps a half grid takes while the other half's bytes cross the bus (24 B in, 16 B out per node
-    // against about 1.4e-11 s per node-step on B200: 28 and 20 steps at 50 GB/s), even
-    const int s_up = 28, s_dn = 20;
-    const int R = n / 2, R_up = R + halo * s_up;
+    // The range that goes first (start) / last (end) is the fraction f of the rows; what stays exposed is ITS transfer,
+    // so f should be small -- but the head start it needs grows as (1 - f) / f: the other range's 24 B (16 B) per node
+    // cross the bus at about 55 GB/s while a node-step takes about 1.45e-11 s, i.e. 29 (19) steps of a range as large
+    // as the one on the bus.  f = 1/4 when the solve is long enough for both head starts (0.8 iters), else up to 1/2.
+    double f = 1.0 / (1.0 + iters / 62.0);
+    f = f < 0.25 ? 0.25 : (f > 0.5 ? 0.5 : f);
+    const int R_top = ((int)(f * n) + 1) & ~1;               // start: rows [0, R_top) go first
+    const int R_dn = n - R_top;                              // end: rows [R_dn, n) leave last
+    int s_up = (int)((1.0 - f) / f * 29.0) & ~1, s_dn = (int)((1.0 - f) / f * 19.0) & ~1;      // even
+    if (s_up + s_dn > (iters * 4) / 5) {
+        const double scale = 0.8 * iters / (s_up + s_dn);
+        s_up = (int)(s_up * scale) & ~1;
+        s_dn = (int)(s_dn * scale) & ~1;
+    }
+    while (s_up > 0 && R_top + halo * s_up > (n * 3) / 4) s_up -= 2;     // the first transfer must stay the smaller one
+    while (s_dn > 0 && R_dn + halo * s_dn > n - halo) s_dn -= 2;         // the head start ends inside the grid
+    const int R_up = R_top + halo * s_up;
     double *d_p, *d_c;
     double2 *d_psi, *d_work;
     NLSB_TRY(mem.alloc(&d_p, np));
@@ -647,18 +661,18 @@ int host_rk4_2d_pipelined(double dt, const CrossWeights &w, int n, int order, in
         return launch_interleaved_step(order, st, w, s);
     };
     NLSB_CUDA(cudaStreamWaitEvent(s, top_in.ev, 0));
-    for (int j = 1; j <= s_up; ++j) NLSB_TRY(range_step(j, 0, R + halo * (s_up - j)));
+    for (int j = 1; j <= s_up; ++j) NLSB_TRY(range_step(j, 0, R_top + halo * (s_up - j)));
     NLSB_CUDA(cudaStreamWaitEvent(s, bot_in.ev, 0));
-    for (int j = 1; j <= s_up; ++j) NLSB_TRY(range_step(j, R + halo * (s_up - j), n));
+    for (int j = 1; j <= s_up; ++j) NLSB_TRY(range_step(j, R_top + halo * (s_up - j), n));
     // middle: whole-grid steps (cached graphs), state in d_psi before and after
     NLSB_TRY(enqueue_rk4_2d(1, n, n, order, iters - s_up - s_dn, dt, w, d_p, d_c, d_psi, d_work, s));
-    for (int j = 1; j <= s_dn; ++j) NLSB_TRY(range_step(j, 0, R + halo * (s_dn - j)));
+    for (int j = 1; j <= s_dn; ++j) NLSB_TRY(range_step(j, 0, R_dn + halo * (s_dn - j)));
     NLSB_CUDA(cudaEventRecord(top_out.ev, s));
     NLSB_CUDA(cudaStreamWaitEvent(c, top_out.ev, 0));
     double2 *h_u = reinterpret_cast<double2 *>(u);
-    NLSB_CUDA(cudaMemcpyAsync(h_u, d_psi, sizeof(double2) * R * row, cudaMemcpyDeviceToHost, c));
-    for (int j = 1; j <= s_dn; ++j) NLSB_TRY(range_step(j, R + halo * (s_dn - j), n));
-    NLSB_CUDA(cudaMemcpyAsync(h_u + R * row, d_psi + R * row, sizeof(double2) * (n - R) * row, cudaMemcpyDeviceToHost, s));
+    NLSB_CUDA(cudaMemcpyAsync(h_u, d_psi, sizeof(double2) * R_dn * row, cudaMemcpyDeviceToHost, c));
+    for (int j = 1; j <= s_dn; ++j) NLSB_TRY(range_step(j, R_dn + halo * (s_dn - j), n));
+    NLSB_CUDA(cudaMemcpyAsync(h_u + R_dn * row, d_psi + R_dn * row, sizeof(double2) * (n - R_dn) * row, cudaMemcpyDeviceToHost, s));
     NLSB_CUDA(cudaStreamSynchronize(c));
     NLSB_CUDA(cudaStreamSynchronize(s));
     return 0;
