@@ -177,6 +177,12 @@ int nlsb_set_2d_path(int path);
  * width = threads per strip (one of the compiled widths; 0 = automatic), iters_per_cta = rows a CTA marches
  * (0 = automatic).  Every setting produces the same bits. */
 int nlsb_set_stream_tuning(int sync, int width, int iters_per_cta);
+/* How nlsb_solve_nls_2d (nls.f90:903-919, host buffers) schedules a solve: overlapped != 0 when the transfers are
+ * overlapped with the first / last steps (grids >= 2048^2, >= 160 steps, automatic or strip-marching kernels).  Start:
+ * rows [0, r_top + 4k s_up) are uploaded first and the range [0, r_top + 4k (s_up - j)) takes step j while the other
+ * rows are on the bus, then the complementary rows catch up; end: the range [0, r_dn + 4k (s_dn - j)) takes step j of the
+ * last s_dn steps first and rows [0, r_dn) leave for the host while the rows below finish.  Host arithmetic only. */
+int nlsb_solve_nls_2d_plan(int n, int order, int iters, int *overlapped, int *r_top, int *s_up, int *r_dn, int *s_dn);
 int nlsb_dev_rk4_2d(int batch, int rows, int cols, int order, int iters, double dt, const double *wx,
                     const double *wy, const double *pumping, const double *coeffs,
                     const double *shared_coeffs_host, double *psi,

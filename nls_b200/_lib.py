@@ -61,6 +61,7 @@ PROTOTYPES = {
     "nlsb_dev_rk4_2d_workspace": (_Z, [_I, _I, _I]),
     "nlsb_set_2d_path": (_I, [_I]),
     "nlsb_set_stream_tuning": (_I, [_I, _I, _I]),
+    "nlsb_solve_nls_2d_plan": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
     "nlsb_dev_rk4_2d": (_I, [_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "nlsb_dev_rk4_step_2d_slab": (_I, [_I, _I, _I, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "nlsb_planar_pitch": (_I, [_I]),

@@ -597,10 +597,40 @@ bool pipelined_solve_applies(int n, int order, int iters)
 {
     const int path = g_path_2d.load();
     if (path != 0 && path != 8) return false;
-    const int halo = 2 * (order - 1);          // 4k rows per step
-    // both row ranges must be grids the strip-marching kernel takes (>= 2^20 nodes, even column count) and the
-    // head start must stay a small part of the range
-    return (n & 1) == 0 && (long long)(n / 4) * n >= (1ll << 20) && iters >= 160 && 28 * halo <= n / 8;
+    (void)order;
+    // every row range must be a grid the strip-marching kernel takes (>= 2^20 nodes, even column count); pipeline_plan
+    // keeps the head starts inside the grid whatever the order
+    return (n & 1) == 0 && (long long)(n / 4) * n >= (1ll << 20) && iters >= 160;
+}
+
+// Split points and head starts of the overlapped solve (host arithmetic only; also behind nlsb_solve_nls_2d_plan).
+struct PipelinePlan {
+    int r_top, s_up;     // start: rows [0, r_top + 4k s_up) are uploaded first; the top range takes s_up steps ahead
+    int r_dn, s_dn;      // end: the range [0, r_dn) takes s_dn steps ahead and leaves first; rows [r_dn, n) leave last
+};
+
+PipelinePlan pipeline_plan(int n, int order, int iters)
+{
+    const int halo = 2 * (order - 1);
+    // The range that goes first (start) / last (end) is the fraction f of the rows; what stays exposed is ITS transfer,
+    // so f should be small -- but the head start it needs grows as (1 - f) / f: the other range's 24 B (16 B) per node
+    // cross the bus at about 55 GB/s while a node-step takes about 1.45e-11 s, i.e. 29 (19) steps of a range as large
+    // as the one on the bus.  f = 1/4 when the solve is long enough for both head starts (0.8 iters), else up to 1/2.
+    double f = 1.0 / (1.0 + iters / 62.0);
+    f = f < 0.25 ? 0.25 : (f > 0.5 ? 0.5 : f);
+    PipelinePlan p;
+    p.r_top = ((int)(f * n) + 1) & ~1;
+    p.r_dn = n - p.r_top;
+    p.s_up = (int)((1.0 - f) / f * 29.0) & ~1;       // even: the middle part starts and ends in `psi`
+    p.s_dn = (int)((1.0 - f) / f * 19.0) & ~1;
+    if (p.s_up + p.s_dn > (iters * 4) / 5) {
+        const double scale = 0.8 * iters / (p.s_up + p.s_dn);
+        p.s_up = (int)(p.s_up * scale) & ~1;
+        p.s_dn = (int)(p.s_dn * scale) & ~1;
+    }
+    while (p.s_up > 0 && p.r_top + halo * p.s_up > (n * 3) / 4) p.s_up -= 2;   // the first transfer stays the smaller one
+    while (p.s_dn > 0 && p.r_dn + halo * p.s_dn > n - halo) p.s_dn -= 2;       // the head start ends inside the grid
+    return p;
 }
 
 int host_rk4_2d_pipelined(double dt, const CrossWeights &w, int n, int order, int iters, const double *pumping,
@@ -616,22 +646,8 @@ int host_rk4_2d_pipelined(double dt, const CrossWeights &w, int n, int order, in
     } drain{c};
     const size_t np = (size_t)n * n, row = (size_t)n;
     const int halo = 2 * (order - 1);
-    // The range that goes first (start) / last (end) is the fraction f of the rows; what stays exposed is ITS transfer,
-    // so f should be small -- but the head start it needs grows as (1 - f) / f: the other range's 24 B (16 B) per node
-    // cross the bus at about 55 GB/s while a node-step takes about 1.45e-11 s, i.e. 29 (19) steps of a range as large
-    // as the one on the bus.  f = 1/4 when the solve is long enough for both head starts (0.8 iters), else up to 1/2.
-    double f = 1.0 / (1.0 + iters / 62.0);
-    f = f < 0.25 ? 0.25 : (f > 0.5 ? 0.5 : f);
-    const int R_top = ((int)(f * n) + 1) & ~1;               // start: rows [0, R_top) go first
-    const int R_dn = n - R_top;                              // end: rows [R_dn, n) leave last
-    int s_up = (int)((1.0 - f) / f * 29.0) & ~1, s_dn = (int)((1.0 - f) / f * 19.0) & ~1;      // even
-    if (s_up + s_dn > (iters * 4) / 5) {
-        const double scale = 0.8 * iters / (s_up + s_dn);
-        s_up = (int)(s_up * scale) & ~1;
-        s_dn = (int)(s_dn * scale) & ~1;
-    }
-    while (s_up > 0 && R_top + halo * s_up > (n * 3) / 4) s_up -= 2;     // the first transfer must stay the smaller one
-    while (s_dn > 0 && R_dn + halo * s_dn > n - halo) s_dn -= 2;         // the head start ends inside the grid
+    const PipelinePlan plan = pipeline_plan(n, order, iters);
+    const int R_top = plan.r_top, R_dn = plan.r_dn, s_up = plan.s_up, s_dn = plan.s_dn;
     const int R_up = R_top + halo * s_up;
     double *d_p, *d_c;
     double2 *d_psi, *d_work;
@@ -860,6 +876,16 @@ int nlsb_trim_memory(void)
             cudaError_t e = cudaMemPoolTrimTo(g_pools[dev], 0);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemPoolTrimTo");
         }
+    return 0;
+}
+
+int nlsb_solve_nls_2d_plan(int n, int order, int iters, int *overlapped, int *r_top, int *s_up, int *r_dn, int *s_dn)
+{
+    if (!overlapped || !r_top || !s_up || !r_dn || !s_dn) return fail(NLSB_EINVAL, "solve_nls_2d_plan: null argument");
+    NLSB_TRY(check_order_size(n, order));
+    *overlapped = pipelined_solve_applies(n, order, iters) ? 1 : 0;
+    const PipelinePlan p = pipeline_plan(n, order, iters);
+    *r_top = p.r_top; *s_up = p.s_up; *r_dn = p.r_dn; *s_dn = p.s_dn;
     return 0;
 }
 
