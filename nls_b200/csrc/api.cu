@@ -567,8 +567,9 @@ int host_rk4_1d(double dt, const double *taps_host, int n, int order, int iters,
 //          [0, R' + 4k (s' - j))) and leaves for the host while the bottom range takes its last s' steps.
 // Both ranges ping-pong between the same two buffers; a range's step j never overwrites rows the other range's step j
 // still reads (they lie 4k rows beyond its edge).  Bit-identical to the plain loop; s, s' are even so that the middle
-// part starts and ends in `psi`.  With pageable host memory the copies do not overlap anything (cudaMemcpyAsync stages
-// them synchronously) and the scheme costs the 4k s redundant rows of the catch-up ranges' neighbours only.
+// part starts and ends in `psi`.  No node is computed twice (the two ranges of a step are complementary), so with
+// pageable host memory -- whose copies cudaMemcpyAsync stages synchronously: nothing overlaps -- the scheme costs only
+// its extra launches.
 int copy_stream(cudaStream_t *out)
 {
     static thread_local cudaStream_t streams[64] = {};
